@@ -1,0 +1,130 @@
+"""ctypes binding of libea_b200.so (the C ABI declared in include/ea_b200.h).
+
+The library is built in-tree by ``easyanimate_b200/csrc/build.sh`` (``__graft_entry__.build()``).  There is no
+CPU or PyTorch fallback: if the shared object is missing the import of any product module fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libea_b200.so")
+
+
+class EaError(RuntimeError):
+    pass
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'"
+            " or easyanimate_b200/csrc/build.sh). easyanimate_b200 has no CPU/PyTorch fallback."
+        )
+    return C.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+i64, i32, f32, vp = C.c_int64, C.c_int32, C.c_float, C.c_void_p
+
+# epilogues (keep in sync with include/ea_b200.h)
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RES, EPI_SCALE_F32, EPI_BIAS_RES = 0, 1, 2, 3, 4
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("a", vp), ("w", vp), ("bias", vp), ("out", vp),
+        ("M", i64), ("N", i64), ("K", i64),
+        ("lda", i64), ("ldw", i64), ("ldo", i64),
+        ("epilogue", i32), ("scale", f32),
+        ("residual", vp), ("ldr", i64),
+        ("gate", vp), ("gate_stride", i64), ("rows_per_batch", i64),
+    ]
+
+
+class QkvArgs(C.Structure):
+    _fields_ = [
+        ("a", vp), ("w", vp), ("bias", vp),
+        ("ln_q_w", vp), ("ln_q_b", vp), ("ln_k_w", vp), ("ln_k_b", vp),
+        ("rope_cos", vp), ("rope_sin", vp),
+        ("q", vp), ("k", vp), ("v", vp),
+        ("M", i64), ("d", i64), ("lda", i64),
+        ("rows_per_batch", i64), ("S", i64), ("seq_offset", i64),
+        ("ln_eps", f32),
+    ]
+
+
+class SkinnyArgs(C.Structure):
+    _fields_ = [
+        ("x", vp), ("w", vp), ("bias", vp), ("out", vp),
+        ("M", i64), ("N", i64), ("K", i64),
+        ("act_in", i32), ("act_out", i32),
+    ]
+
+
+class LnArgs(C.Structure):
+    _fields_ = [
+        ("x", vp), ("y", vp),
+        ("rows", i64), ("d", i64), ("ldx", i64), ("ldy", i64), ("rows_per_batch", i64),
+        ("pre_w", vp), ("pre_b", vp), ("pre_eps", f32),
+        ("w", vp), ("b", vp), ("eps", f32),
+        ("shift", vp), ("scale", vp), ("mod_stride", i64),
+    ]
+
+
+class RmsArgs(C.Structure):
+    _fields_ = [("x", vp), ("y", vp), ("w", vp), ("rows", i64), ("d", i64), ("eps", f32)]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("q", vp), ("k", vp), ("v", vp),
+        ("out_text", vp), ("out_video", vp),
+        ("B", i64), ("H", i64), ("S", i64), ("S_text", i64),
+        ("scale", f32),
+    ]
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [
+        ("x", vp), ("w", vp), ("bias", vp), ("residual", vp), ("out", vp),
+        ("N", i64), ("T", i64), ("H", i64), ("W", i64), ("Cin", i64), ("Cout", i64),
+        ("upsample", i32), ("out_nchw", i32), ("ldo_c", i64),
+    ]
+
+
+class GnArgs(C.Structure):
+    _fields_ = [
+        ("x", vp), ("y", vp), ("gamma", vp), ("beta", vp), ("stats", vp),
+        ("frames", i64), ("HW", i64), ("C", i64), ("groups", i64),
+        ("eps", f32), ("silu", i32),
+    ]
+
+
+def _sig(name, argtypes, restype=C.c_int):
+    fn = getattr(lib, name)
+    fn.argtypes = argtypes
+    fn.restype = restype
+    return fn
+
+
+ea_last_error = _sig("ea_last_error", [], C.c_char_p)
+ea_abi_version = _sig("ea_abi_version", [])
+ea_launch_count = _sig("ea_launch_count", [], C.c_uint64)
+ea_gemm = _sig("ea_gemm", [C.POINTER(GemmArgs), vp])
+ea_qkv_gemm_ln_rope = _sig("ea_qkv_gemm_ln_rope", [C.POINTER(QkvArgs), vp])
+ea_skinny_linear = _sig("ea_skinny_linear", [C.POINTER(SkinnyArgs), vp])
+ea_layernorm_modulate = _sig("ea_layernorm_modulate", [C.POINTER(LnArgs), vp])
+ea_rmsnorm = _sig("ea_rmsnorm", [C.POINTER(RmsArgs), vp])
+ea_timestep_embedding = _sig("ea_timestep_embedding", [vp, vp, i64, i64, f32, i32, vp])
+ea_patchify = _sig("ea_patchify", [vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, vp])
+ea_unpatchify = _sig("ea_unpatchify", [vp, vp, i64, i64, i64, i64, i64, i64, vp])
+ea_cfg_euler_step = _sig("ea_cfg_euler_step", [vp, vp, vp, vp, i64, f32, i32, f32, f32, vp])
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = ea_last_error()
+        raise EaError(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")

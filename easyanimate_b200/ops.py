@@ -1,0 +1,168 @@
+"""Torch-tensor front end of the C ABI: each function checks shapes/dtypes, hands raw device pointers and the
+current CUDA stream to ``libea_b200.so`` and returns torch tensors it allocated.  PyTorch is only the allocator and
+the stream owner here; none of these functions computes anything with torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+bf16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype=bf16, name="tensor"):
+    if not t.is_cuda:
+        raise L.EaError(f"{name} must be a CUDA tensor (easyanimate_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise L.EaError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, epilogue: int = L.EPI_BIAS,
+         out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+         gate: Optional[torch.Tensor] = None, rows_per_batch: int = 0, scale: float = 1.0) -> torch.Tensor:
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T + bias). a/w may be row-strided views (last dim contiguous)."""
+    _req(a, name="a"); _req(w, name="w")
+    assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1], (a.shape, w.shape)
+    assert a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32 if epilogue == L.EPI_SCALE_F32 else bf16)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    args = L.GemmArgs(
+        a=_p(a), w=_p(w), bias=_p(bias), out=_p(out), M=M, N=N, K=K,
+        lda=a.stride(0), ldw=w.stride(0), ldo=out.stride(0), epilogue=epilogue, scale=scale,
+        residual=_p(residual), ldr=residual.stride(0) if residual is not None else 0,
+        gate=_p(gate), gate_stride=gate.stride(0) if gate is not None else 0, rows_per_batch=rows_per_batch)
+    L.check(L.ea_gemm(C.byref(args), _stream()), "ea_gemm")
+    return out
+
+
+def qkv_gemm_ln_rope(a: torch.Tensor, w_qkv: torch.Tensor, b_qkv: torch.Tensor, ln_q: Tuple[torch.Tensor, torch.Tensor],
+                     ln_k: Tuple[torch.Tensor, torch.Tensor], rope: Optional[Tuple[torch.Tensor, torch.Tensor]],
+                     q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, rows_per_batch: int, seq_offset: int,
+                     eps: float = 1e-6) -> None:
+    """Fused q/k/v projection + per-head LayerNorm + RoPE, written into q/k/v[B,H,S,64] at seq_offset."""
+    _req(a, name="a"); _req(w_qkv, name="w_qkv")
+    M, d = a.shape
+    assert w_qkv.shape == (3 * d, d) and w_qkv.is_contiguous() and b_qkv.shape == (3 * d,)
+    B, H, S, hd = q.shape
+    assert hd == 64 and H * 64 == d and k.shape == q.shape and v.shape == q.shape
+    assert q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
+    cos = sin = None
+    if rope is not None:
+        cos, sin = rope
+        _req(cos, torch.float32, "rope cos"); _req(sin, torch.float32, "rope sin")
+        assert cos.shape == (rows_per_batch, 64) and sin.shape == cos.shape and cos.is_contiguous() and sin.is_contiguous()
+    args = L.QkvArgs(
+        a=_p(a), w=_p(w_qkv), bias=_p(b_qkv), ln_q_w=_p(ln_q[0]), ln_q_b=_p(ln_q[1]), ln_k_w=_p(ln_k[0]),
+        ln_k_b=_p(ln_k[1]), rope_cos=_p(cos), rope_sin=_p(sin), q=_p(q), k=_p(k), v=_p(v), M=M, d=d, lda=a.stride(0),
+        rows_per_batch=rows_per_batch, S=S, seq_offset=seq_offset, ln_eps=eps)
+    L.check(L.ea_qkv_gemm_ln_rope(C.byref(args), _stream()), "ea_qkv_gemm_ln_rope")
+
+
+def skinny_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, act_in: int = 0,
+                  act_out: int = 0) -> torch.Tensor:
+    _req(x, name="x"); _req(w, name="w")
+    M, K = x.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and x.is_contiguous() and w.is_contiguous()
+    out = torch.empty((M, N), device=x.device, dtype=bf16)
+    args = L.SkinnyArgs(x=_p(x), w=_p(w), bias=_p(bias), out=_p(out), M=M, N=N, K=K, act_in=act_in, act_out=act_out)
+    L.check(L.ea_skinny_linear(C.byref(args), _stream()), "ea_skinny_linear")
+    return out
+
+
+def layernorm_modulate(x: torch.Tensor, w: Optional[torch.Tensor], b: Optional[torch.Tensor], eps: float, *,
+                       shift: Optional[torch.Tensor] = None, scale: Optional[torch.Tensor] = None,
+                       rows_per_batch: int = 0, pre: Optional[Tuple[torch.Tensor, torch.Tensor, float]] = None,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x: [rows, d] (row stride free). shift/scale: [B, d] views (row stride free, last dim contiguous)."""
+    _req(x, name="x")
+    rows, d = x.shape
+    assert x.stride(1) == 1
+    if out is None:
+        out = torch.empty((rows, d), device=x.device, dtype=bf16)
+    mod_stride = 0
+    if shift is not None:
+        assert scale is not None and shift.stride(0) == scale.stride(0) and shift.stride(1) == 1
+        mod_stride = shift.stride(0)
+    args = L.LnArgs(
+        x=_p(x), y=_p(out), rows=rows, d=d, ldx=x.stride(0), ldy=out.stride(0), rows_per_batch=rows_per_batch,
+        pre_w=_p(pre[0]) if pre else None, pre_b=_p(pre[1]) if pre else None, pre_eps=pre[2] if pre else 0.0,
+        w=_p(w), b=_p(b), eps=eps, shift=_p(shift), scale=_p(scale), mod_stride=mod_stride)
+    L.check(L.ea_layernorm_modulate(C.byref(args), _stream()), "ea_layernorm_modulate")
+    return out
+
+
+def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
+    _req(x, name="x")
+    rows, d = x.shape
+    assert x.is_contiguous()
+    out = torch.empty_like(x)
+    args = L.RmsArgs(x=_p(x), y=_p(out), w=_p(w), rows=rows, d=d, eps=eps)
+    L.check(L.ea_rmsnorm(C.byref(args), _stream()), "ea_rmsnorm")
+    return out
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, flip_sin_to_cos: bool = True, freq_shift: float = 0.0) -> torch.Tensor:
+    _req(t, name="timestep")
+    out = torch.empty((t.shape[0], dim), device=t.device, dtype=bf16)
+    L.check(L.ea_timestep_embedding(_p(t), _p(out), t.shape[0], dim, freq_shift, int(flip_sin_to_cos), _stream()),
+            "ea_timestep_embedding")
+    return out
+
+
+def patchify(x: torch.Tensor, x2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[B,C,F,H,W] (+ optional channel-concat source) -> A[B*F*(H/2)*(W/2), ld] with ld = 4C rounded up to 8."""
+    _req(x, name="latents")
+    B, C1, F, H, W = x.shape
+    C2 = 0
+    if x2 is not None:
+        _req(x2, name="inpaint latents")
+        assert x2.shape[0] == B and x2.shape[2:] == x.shape[2:]
+        C2 = x2.shape[1]
+        x2 = x2.contiguous()
+    x = x.contiguous()
+    kvalid = 4 * (C1 + C2)
+    ldk = (kvalid + 7) // 8 * 8
+    a = torch.empty((B * F * (H // 2) * (W // 2), ldk), device=x.device, dtype=bf16)
+    L.check(L.ea_patchify(_p(x), _p(x2), _p(a), B, C1, C2, F, H, W, ldk, _stream()), "ea_patchify")
+    return a
+
+
+def unpatchify(y: torch.Tensor, B: int, C: int, F: int, H: int, W: int) -> torch.Tensor:
+    _req(y, name="proj_out output")
+    out = torch.empty((B, C, F, H, W), device=y.device, dtype=bf16)
+    L.check(L.ea_unpatchify(_p(y), _p(out), B, C, F, H, W, y.stride(0), _stream()), "ea_unpatchify")
+    return out
+
+
+def cfg_euler_step(noise_pred: torch.Tensor, latents: torch.Tensor, guidance_scale: float, sigma: float,
+                   sigma_next: float, use_cfg: bool = True) -> torch.Tensor:
+    """noise_pred: [2B,...] (uncond first, then text) when use_cfg else [B,...]; latents [B,...]."""
+    _req(noise_pred, name="noise_pred"); _req(latents, name="latents")
+    noise_pred = noise_pred.contiguous(); latents = latents.contiguous()
+    n = latents.numel()
+    out = torch.empty_like(latents)
+    if use_cfg:
+        assert noise_pred.numel() == 2 * n
+        pu, pt = noise_pred.data_ptr(), noise_pred.data_ptr() + n * 2
+    else:
+        assert noise_pred.numel() == n
+        pu, pt = noise_pred.data_ptr(), None
+    L.check(L.ea_cfg_euler_step(pu, pt, _p(latents), _p(out), n, guidance_scale, int(use_cfg), sigma, sigma_next,
+                                _stream()), "ea_cfg_euler_step")
+    return out

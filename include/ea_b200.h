@@ -1,0 +1,172 @@
+/*
+ * libea_b200.so — C ABI of the B200-native (sm_100a) kernels behind EasyAnimateV5.1's sampling hot path.
+ *
+ * The reference (aigc-apps/EasyAnimate @ c2a70d1) is 100 % Python: its "operator interface" for this path is the
+ * list of torch library calls made by EasyAnimateTransformer3DModel.forward (easyanimate/models/transformer3d.py:1496-1689),
+ * EasyAnimateDiTBlock.forward (easyanimate/models/attention.py:1107-1163), EasyAnimateAttnProcessor2_0.__call__
+ * (easyanimate/models/processor.py:218-312), EasyAnimateLayerNormZero.forward (easyanimate/models/norm.py:160-166)
+ * and AutoencoderKLMagvit.decode (easyanimate/models/autoencoder_magvit.py:271-317, 381-448) /
+ * Decoder.forward (easyanimate/vae/ldm/models/omnigen_enc_dec.py:555-677).  Each entry point below names the
+ * reference call sites it replaces.
+ *
+ * Conventions
+ *  - every function only ENQUEUES work on `stream` (a cudaStream_t passed as void*): no allocation, no
+ *    synchronisation, no global state; safe to capture in a CUDA graph.
+ *  - all pointers are device pointers unless stated otherwise; activations/weights are bf16 unless stated.
+ *  - return value 0 = ok, negative = error; `ea_last_error()` returns a thread-local message.
+ *  - no torch types cross this boundary.
+ */
+#ifndef EA_B200_H_
+#define EA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EA_OK 0
+#define EA_ERR_INVALID (-1)
+#define EA_ERR_CUDA (-2)
+#define EA_ERR_WORKSPACE (-3)
+
+const char* ea_last_error(void);
+int ea_abi_version(void);
+/* number of kernels launched through this library since load (bench.py's gpu_launches counter) */
+uint64_t ea_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Dense contraction on tcgen05 tensor cores:  out[M,N] = epilogue(A[M,K] · W[N,K]^T + bias[N])
+ * Replaces every nn.Linear on the path (F.linear -> cuBLAS in the reference): processor.py:244-246,261-263,303-311
+ * (q/k/v/out projections), diffusers FeedForward built at attention.py:1082-1100 (net.0.proj, net.2),
+ * transformer3d.py:1402-1404 (patch-embed Conv2d == GEMM over 2x2 patches), :1410-1413 (text_proj Linear),
+ * :1680 (proj_out); VAE 1x1x1 convs (autoencoder_magvit.py:182,281; common.py:291-294) and the VAE
+ * mid-block attention projections (attention_processors.py:105-131).
+ * A, W are K-major bf16 (row strides lda/ldw in elements, multiples of 8). fp32 accumulation in TMEM.
+ * ------------------------------------------------------------------------------------------------------------ */
+enum {
+  EA_EPI_BIAS = 0,          /* out = bf16(acc + bias)                                                       */
+  EA_EPI_BIAS_GELU = 1,     /* out = bf16(gelu_tanh(bf16(acc + bias)))            (FeedForward net.0)       */
+  EA_EPI_BIAS_GATE_RES = 2, /* out = bf16(res + bf16(gate[b] * bf16(acc + bias))) (attention.py:1140-41,1161-62) */
+  EA_EPI_SCALE_F32 = 3,     /* out(fp32) = scale * acc                            (VAE attention scores)    */
+  EA_EPI_BIAS_RES = 4,      /* out = bf16(bf16(acc + bias) + res)                 (VAE shortcut / attn residual) */
+};
+
+typedef struct {
+  const void* a;        /* [M,K] bf16 */
+  const void* w;        /* [N,K] bf16 */
+  const void* bias;     /* [N] bf16 or NULL */
+  void* out;            /* [M,N] bf16 (fp32 for EA_EPI_SCALE_F32) */
+  int64_t M, N, K;
+  int64_t lda, ldw, ldo;
+  int32_t epilogue;
+  float scale;            /* EA_EPI_SCALE_F32 */
+  const void* residual;   /* [M,N] bf16, row stride ldr (GATE_RES, BIAS_RES) */
+  int64_t ldr;
+  const void* gate;       /* [batch, N] bf16, row stride gate_stride; batch = row / rows_per_batch (GATE_RES) */
+  int64_t gate_stride;
+  int64_t rows_per_batch;
+} ea_gemm_args;
+
+int ea_gemm(const ea_gemm_args* args, void* stream);
+
+/* Fused Q/K/V projection: A[M,d] · Wqkv[3d,d]^T + bias, then per-head LayerNorm(64) on q,k (affine, eps),
+ * 3-D RoPE on q,k for video rows, written head-major into q/k/v[B,H,S,64] at sequence offset seq_offset.
+ * Replaces processor.py:244-285 (to_q/to_k/to_v, view/transpose, norm_q/norm_k, cat, apply_rotary_emb).
+ * M = B * rows_per_batch (rows_per_batch = S_text or S_video). d = H*64. */
+typedef struct {
+  const void* a;          /* [M,d] bf16, row stride lda */
+  const void* w;          /* [3d,d] bf16: rows [0,d)=to_q, [d,2d)=to_k, [2d,3d)=to_v */
+  const void* bias;       /* [3d] bf16 */
+  const void* ln_q_w;     /* [64] bf16 (norm_q.weight) */
+  const void* ln_q_b;
+  const void* ln_k_w;
+  const void* ln_k_b;
+  const float* rope_cos;  /* [rows_per_batch,64] fp32 or NULL (text rows: no RoPE) */
+  const float* rope_sin;
+  void* q;                /* [B,H,S,64] bf16 */
+  void* k;
+  void* v;
+  int64_t M, d, lda;
+  int64_t rows_per_batch; /* S_part */
+  int64_t S;              /* total sequence length of q/k/v */
+  int64_t seq_offset;     /* where this part's rows start inside S */
+  float ln_eps;
+} ea_qkv_args;
+
+int ea_qkv_gemm_ln_rope(const ea_qkv_args* args, void* stream);
+
+/* Small-M linear (M <= 8), one warp per output feature: out[M,N] = act(x)[M,K] · W[N,K]^T + bias.
+ * Replaces norm.py:163 (Linear(512->6d) on SiLU(temb)), diffusers AdaLayerNorm linear (transformer3d.py:1472-1478),
+ * TimestepEmbedding linear_1/linear_2 (transformer3d.py:1399-1400,1519-1520).
+ * act_in: 0 none, 1 SiLU on the input; act_out: 0 none, 1 SiLU on the output (both with bf16 rounding points
+ * matching the reference's op-by-op bf16 execution). */
+typedef struct {
+  const void* x;    /* [M,K] bf16 */
+  const void* w;    /* [N,K] bf16 */
+  const void* bias; /* [N] bf16 or NULL */
+  void* out;        /* [M,N] bf16 */
+  int64_t M, N, K;
+  int32_t act_in, act_out;
+} ea_skinny_linear_args;
+
+int ea_skinny_linear(const ea_skinny_linear_args* args, void* stream);
+
+/* y = [modulate]( LN( [LN_pre](x) ) ): row-wise LayerNorm over d with fp32 statistics, bf16 output, optionally
+ * preceded by a first affine LayerNorm and followed by AdaLN modulation y*(1+scale[b])+shift[b].
+ * Replaces EasyAnimateLayerNormZero.forward (norm.py:160-166, FP32LayerNorm norm.py:16-26) for both streams, and the
+ * tail transformer3d.py:1673-1678 (norm_final -> norm_out AdaLayerNorm) with pre_* = norm_final. */
+typedef struct {
+  const void* x;
+  void* y;
+  int64_t rows, d, ldx, ldy;
+  int64_t rows_per_batch; /* batch index of a row = row / rows_per_batch (selects the shift/scale row) */
+  const void* pre_w;      /* optional first LayerNorm affine [d] (NULL = skip) */
+  const void* pre_b;
+  float pre_eps;
+  const void* w;          /* LayerNorm affine [d] or NULL */
+  const void* b;
+  float eps;
+  const void* shift;      /* [B, mod_stride] bf16 or NULL */
+  const void* scale;
+  int64_t mod_stride;
+} ea_ln_args;
+
+int ea_layernorm_modulate(const ea_ln_args* args, void* stream);
+
+/* EasyAnimateRMSNorm (norm.py:28-39): y = w * bf16(x * rsqrt(mean(x^2) + eps)) */
+typedef struct {
+  const void* x;
+  void* y;
+  const void* w;
+  int64_t rows, d;
+  float eps;
+} ea_rmsnorm_args;
+
+int ea_rmsnorm(const ea_rmsnorm_args* args, void* stream);
+
+/* diffusers Timesteps(dim, flip_sin_to_cos, freq_shift) on a bf16 timestep vector t[B] -> out[B,dim] bf16
+ * (transformer3d.py:1399,1519; the pipeline rounds t to bf16 first, pipeline_easyanimate.py:1079-1081). */
+int ea_timestep_embedding(const void* t, void* out, int64_t B, int64_t dim, float freq_shift,
+                          int32_t flip_sin_to_cos, void* stream);
+
+/* Patch-embed im2col for kernel=stride=2 (transformer3d.py:1523-1531): A[(b,f,hh,ww), c*4+ph*2+pw] =
+ * cat(x[B,C1,F,H,W], x2[B,C2,F,H,W])[b,c,f,2hh+ph,2ww+pw]; row stride ldk (columns >= 4(C1+C2) zero-filled). */
+int ea_patchify(const void* x, const void* x2, void* a, int64_t B, int64_t C1, int64_t C2, int64_t F, int64_t H,
+                int64_t W, int64_t ldk, void* stream);
+
+/* Unpatchify (transformer3d.py:1683-1685): out[B,C,F,H,W] from y[(b,f,hh,ww), c*4+ph*2+pw], row stride ldy. */
+int ea_unpatchify(const void* y, void* out, int64_t B, int64_t C, int64_t F, int64_t H, int64_t W, int64_t ldy,
+                  void* stream);
+
+/* Classifier-free-guidance combine + FlowMatchEuler step (pipeline_easyanimate.py:1102-1111; diffusers
+ * FlowMatchEulerDiscreteScheduler.step): v = u + g*(c-u); x_out = bf16(float(x) + bf16(bf16(sigma_next-sigma)*v)).
+ * n elements (even). use_cfg=0: v = pred_uncond. */
+int ea_cfg_euler_step(const void* pred_uncond, const void* pred_text, const void* x, void* x_out, int64_t n,
+                      float guidance_scale, int32_t use_cfg, float sigma, float sigma_next, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EA_B200_H_ */
