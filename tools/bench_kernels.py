@@ -1,0 +1,43 @@
+"""Micro-benchmarks of individual kernels (CUDA events, L2-flushed between reps). Usage: python tools/bench_kernels.py gemm|attn|conv"""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+bf16 = torch.bfloat16
+
+
+def timeit(fn, reps=10, warmup=3, flush=True):
+    scratch = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda") if flush else None
+    for _ in range(warmup):
+        fn()
+    ts = []
+    for _ in range(reps):
+        if flush:
+            scratch.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record(); torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def bench_gemm():
+    from easyanimate_b200 import ops, _lib as L
+    shapes = [(8192, 8192, 8192), (46800, 3072, 3072), (46800, 12288, 3072), (46800, 3072, 12288), (46800, 9216, 3072),
+              (512, 3072, 3072), (4096, 4096, 4096)]
+    for M, N, K in shapes:
+        a = torch.randn(M, K, device="cuda").to(bf16)
+        w = (torch.randn(N, K, device="cuda") * 0.02).to(bf16)
+        b = torch.randn(N, device="cuda").to(bf16)
+        out = torch.empty(M, N, device="cuda", dtype=bf16)
+        med, best = timeit(lambda: ops.gemm(a, w, b, out=out))
+        medt, bestt = timeit(lambda: torch.nn.functional.linear(a, w, b))
+        fl = 2.0 * M * N * K
+        print(json.dumps({"kernel": "gemm_bias", "M": M, "N": N, "K": K, "ms": round(med, 4), "tflops": round(fl / med / 1e9, 1),
+                          "best_tflops": round(fl / best / 1e9, 1), "torch_ms": round(medt, 4),
+                          "torch_tflops": round(fl / medt / 1e9, 1)}), flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "gemm"
+    {"gemm": bench_gemm}[which]()
