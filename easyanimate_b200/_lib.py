@@ -82,8 +82,8 @@ class AttnArgs(C.Structure):
     _fields_ = [
         ("q", vp), ("k", vp), ("v", vp),
         ("out_text", vp), ("out_video", vp),
-        ("B", i64), ("H", i64), ("S", i64), ("S_text", i64),
-        ("scale", f32),
+        ("B", i64), ("H", i64), ("S", i64), ("S_text", i64), ("S_pad", i64), ("head_dim", i64),
+        ("scale", f32), ("variant", i32),
     ]
 
 
@@ -121,6 +121,8 @@ ea_rmsnorm = _sig("ea_rmsnorm", [C.POINTER(RmsArgs), vp])
 ea_timestep_embedding = _sig("ea_timestep_embedding", [vp, vp, i64, i64, f32, i32, vp])
 ea_patchify = _sig("ea_patchify", [vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, vp])
 ea_unpatchify = _sig("ea_unpatchify", [vp, vp, i64, i64, i64, i64, i64, i64, vp])
+ea_attn_fwd = _sig("ea_attn_fwd", [C.POINTER(AttnArgs), vp])
+ea_transpose_v = _sig("ea_transpose_v", [vp, vp, i64, i64, i64, vp])
 ea_cfg_euler_step = _sig("ea_cfg_euler_step", [vp, vp, vp, vp, i64, f32, i32, f32, f32, vp])
 
 

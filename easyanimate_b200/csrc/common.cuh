@@ -33,7 +33,7 @@ EA_DEVICE float2 unpack_bf16x2(uint32_t u) {
 // A kernel that waits on an mbarrier which never completes would hang the GPU box; every wait is
 // bounded and traps (kills the context, surfaces as a CUDA error on the host) instead.
 #ifndef EA_MBAR_SPIN_LIMIT
-#define EA_MBAR_SPIN_LIMIT (1u << 28)
+#define EA_MBAR_SPIN_LIMIT (1u << 24)
 #endif
 
 // ----------------------------------------------------------------------------------------------

@@ -166,3 +166,28 @@ def cfg_euler_step(noise_pred: torch.Tensor, latents: torch.Tensor, guidance_sca
     L.check(L.ea_cfg_euler_step(pu, pt, _p(latents), _p(out), n, guidance_scale, int(use_cfg), sigma, sigma_next,
                                 _stream()), "ea_cfg_euler_step")
     return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, S_text: int, *, scale: Optional[float] = None,
+              variant: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """softmax(q k^T * scale) v for q,k,v [B,H,S,64]; returns (out_text [B,S_text,H*64], out_video [B,S-S_text,H*64])."""
+    _req(q, name="q"); _req(k, name="k"); _req(v, name="v")
+    B, H, S, hd = q.shape
+    assert hd == 64 and k.shape == q.shape and q.is_contiguous() and k.is_contiguous()
+    if scale is None:
+        scale = hd ** -0.5
+    S_pad = 0
+    if variant & 2:
+        S_pad = (S + 7) // 8 * 8
+        vt = torch.empty((B, H, 64, S_pad), device=q.device, dtype=bf16)
+        L.check(L.ea_transpose_v(_p(v.contiguous()), _p(vt), B * H, S, S_pad, _stream()), "ea_transpose_v")
+        v = vt
+    else:
+        assert v.shape == q.shape and v.is_contiguous()
+    out_text = torch.empty((B, S_text, H * 64), device=q.device, dtype=bf16)
+    out_video = torch.empty((B, S - S_text, H * 64), device=q.device, dtype=bf16)
+    args = L.AttnArgs(q=_p(q), k=_p(k), v=_p(v), out_text=_p(out_text) if S_text else None,
+                      out_video=_p(out_video) if S - S_text else None, B=B, H=H, S=S, S_text=S_text, S_pad=S_pad,
+                      head_dim=64, scale=scale, variant=variant)
+    L.check(L.ea_attn_fwd(C.byref(args), _stream()), "ea_attn_fwd")
+    return out_text, out_video

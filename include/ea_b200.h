@@ -166,6 +166,28 @@ int ea_unpatchify(const void* y, void* out, int64_t B, int64_t C, int64_t F, int
 int ea_cfg_euler_step(const void* pred_uncond, const void* pred_text, const void* x, void* x_out, int64_t n,
                       float guidance_scale, int32_t use_cfg, float sigma, float sigma_next, void* stream);
 
+/* Joint text+video self-attention, non-causal, no mask, head_dim 64:  O = softmax(Q K^T * scale) V.
+ * Replaces F.scaled_dot_product_attention + transpose/reshape/split at processor.py:287-303.
+ * q,k,v: [B,H,S,64] bf16 contiguous.  Output is token-major and split at S_text:
+ * out_text[B,S_text,H*64], out_video[B,S-S_text,H*64].
+ * variant bit0: P operand through TMEM instead of shared memory; bit1: v is pre-transposed [B,H,64,S_pad]
+ * (see ea_transpose_v). variant 0 is the default path. */
+typedef struct {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* out_text;
+  void* out_video;
+  int64_t B, H, S, S_text, S_pad, head_dim;
+  float scale;
+  int32_t variant;
+} ea_attn_args;
+
+int ea_attn_fwd(const ea_attn_args* args, void* stream);
+
+/* v[BH,S,64] -> vt[BH,64,S_pad] (columns >= S zero-filled); S_pad % 8 == 0. */
+int ea_transpose_v(const void* v, void* vt, int64_t BH, int64_t S, int64_t S_pad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,32 @@ def bench_gemm():
                           "torch_tflops": round(fl / medt / 1e9, 1)}), flush=True)
 
 
+def bench_attn():
+    from easyanimate_b200 import ops
+    variant = int(os.environ.get("EA_ATTN_VARIANT", "0"))
+    for (B, H, S, St) in [(1, 48, 13312 + 256, 256), (1, 48, 47056, 256)]:
+        q = torch.randn(B, H, S, 64, device="cuda").to(bf16)
+        k = torch.randn(B, H, S, 64, device="cuda").to(bf16)
+        v = torch.randn(B, H, S, 64, device="cuda").to(bf16)
+        fl = 4.0 * B * H * S * S * 64
+        med, best = timeit(lambda: ops.attention(q, k, v, St, variant=variant), reps=5, warmup=2)
+        res = {"kernel": "attn_fwd", "variant": variant, "B": B, "H": H, "S": S, "ms": round(med, 3), "tflops": round(fl / med / 1e9, 1)}
+        try:
+            medt, _ = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v), reps=5, warmup=2)
+            res.update({"torch_sdpa_ms": round(medt, 3), "torch_sdpa_tflops": round(fl / medt / 1e9, 1)})
+        except Exception as e:  # noqa
+            res["torch_sdpa_error"] = str(e)[:100]
+        try:
+            from flash_attn import flash_attn_func
+            qf, kf, vf = [t.transpose(1, 2).contiguous() for t in (q, k, v)]
+            medf, _ = timeit(lambda: flash_attn_func(qf, kf, vf), reps=5, warmup=2)
+            res.update({"flash_attn2_ms": round(medf, 3), "flash_attn2_tflops": round(fl / medf / 1e9, 1)})
+        except Exception as e:  # noqa
+            res["flash_attn2_error"] = str(e)[:100]
+        print(json.dumps(res), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "gemm"
-    {"gemm": bench_gemm}[which]()
+    {"gemm": bench_gemm, "attn": bench_attn}[which]()
+
