@@ -468,7 +468,7 @@ extern "C" int ea_qkv_gemm_ln_rope(const ea_qkv_args* g, void* stream_) {
   EA_REQUIRE(g != nullptr, "ea_qkv: null args");
   EA_REQUIRE(g->a && g->w && g->bias && g->q && g->k && g->v, "ea_qkv: null pointer");
   EA_REQUIRE(g->ln_q_w && g->ln_q_b && g->ln_k_w && g->ln_k_b, "ea_qkv: null LayerNorm parameter");
-  EA_REQUIRE(g->d > 0 && g->d % 256 == 0, "ea_qkv: d must be a multiple of 256 (4 heads of 64 per tile)");
+  EA_REQUIRE(g->d > 0 && g->d % 64 == 0, "ea_qkv: d must be a multiple of the head size 64");
   EA_REQUIRE(g->M > 0 && g->rows_per_batch > 0 && g->M % g->rows_per_batch == 0, "ea_qkv: M must be B*rows_per_batch");
   EA_REQUIRE(g->lda % 8 == 0 && g->lda >= g->d, "ea_qkv: bad lda");
   EA_REQUIRE(g->seq_offset >= 0 && g->seq_offset + g->rows_per_batch <= g->S, "ea_qkv: part does not fit in S");
@@ -482,5 +482,8 @@ extern "C" int ea_qkv_gemm_ln_rope(const ea_qkv_args* g, void* stream_) {
   p.q = reinterpret_cast<bf16*>(g->q); p.k = reinterpret_cast<bf16*>(g->k); p.v = reinterpret_cast<bf16*>(g->v);
   p.d = (int)g->d; p.heads = (int)(g->d / 64); p.S = (int)g->S; p.seq_offset = (int)g->seq_offset;
   p.rows_per_batch = (int)g->rows_per_batch; p.ln_eps = g->ln_eps;
-  return launch_gemm<256, EPI_QKV>(g->a, g->lda, g->w, g->d, p, stream);
+  // an N tile must not straddle the q|k|v boundaries: the widest tile that divides d
+  if (g->d % 256 == 0) return launch_gemm<256, EPI_QKV>(g->a, g->lda, g->w, g->d, p, stream);
+  if (g->d % 128 == 0) return launch_gemm<128, EPI_QKV>(g->a, g->lda, g->w, g->d, p, stream);
+  return launch_gemm<64, EPI_QKV>(g->a, g->lda, g->w, g->d, p, stream);
 }

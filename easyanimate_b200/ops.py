@@ -169,7 +169,7 @@ def cfg_euler_step(noise_pred: torch.Tensor, latents: torch.Tensor, guidance_sca
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, S_text: int, *, scale: Optional[float] = None,
-              variant: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+              variant: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
     """softmax(q k^T * scale) v for q,k,v [B,H,S,64]; returns (out_text [B,S_text,H*64], out_video [B,S-S_text,H*64])."""
     _req(q, name="q"); _req(k, name="k"); _req(v, name="v")
     B, H, S, hd = q.shape

@@ -1,0 +1,87 @@
+"""easyanimate_b200.EasyAnimateTransformer3DModel against the oracle restatement of the reference (oracle/dit.py)."""
+import pytest
+import torch
+
+from tests.parity import three_way
+
+pytestmark = pytest.mark.gpu
+bf16 = torch.bfloat16
+
+
+def _build(cfg, seed=1234):
+    from oracle import dit
+    from easyanimate_b200.transformer3d import EasyAnimateTransformer3DModel
+    o32 = dit.init_weights_(dit.OracleTransformer3D(**cfg), seed)
+    ob = dit.OracleTransformer3D(**cfg).to(bf16)
+    ob.load_state_dict({k: v.to(bf16) for k, v in o32.state_dict().items()})
+    o32.load_state_dict({k: v.float() for k, v in ob.state_dict().items()})  # truth uses the bf16-rounded weights
+    ours = EasyAnimateTransformer3DModel(**cfg).to(bf16)
+    missing, unexpected = ours.load_state_dict(ob.state_dict(), strict=True)
+    return o32, ob, ours.cuda()
+
+
+def _inputs(B, C, F, H, W, S_t, E, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    lat = torch.randn(B, C, F, H, W, generator=g)
+    enc = torch.randn(B, S_t, E, generator=g) * 3.0
+    t = torch.tensor([937.0, 421.0][:B])
+    return lat, enc, t
+
+
+CFG_TINY = dict(num_attention_heads=2, attention_head_dim=64, in_channels=16, out_channels=16, patch_size=2, num_layers=2,
+                time_embed_dim=64, add_norm_text_encoder=True, text_embed_dim=128, text_embed_dim_t5=None)
+# BASELINE.json configs[0]: single DiT block, d=3072/48 heads, 1 frame 16x16 latent, 256 text tokens of width 3584
+CFG_BLOCK = dict(num_attention_heads=48, attention_head_dim=64, in_channels=16, out_channels=16, patch_size=2, num_layers=1,
+                 time_embed_dim=512, add_norm_text_encoder=True, text_embed_dim=3584, text_embed_dim_t5=None)
+
+
+@pytest.mark.parametrize("name,cfg,shape", [
+    ("tiny_2blocks", CFG_TINY, (2, 16, 3, 8, 12, 40)),
+    ("tiny_ragged", CFG_TINY, (1, 16, 2, 6, 10, 7)),
+    ("config1_single_block", CFG_BLOCK, (2, 16, 1, 16, 16, 256)),
+])
+def test_transformer_forward_matches_oracle(name, cfg, shape):
+    from oracle import dit
+    B, C, F, H, W, S_t = shape
+    o32, ob, ours = _build(cfg)
+    lat, enc, t = _inputs(B, C, F, H, W, S_t, cfg["text_embed_dim"])
+    rope = dit.rope_for_video(H * 8, W * 8, F)
+    with torch.no_grad():
+        # the pipeline rounds the timestep to bf16 before the transformer call (pipeline_easyanimate.py:1079-1081)
+        tb = t.to(bf16)
+        truth = o32(lat.to(bf16).float(), tb.float(), encoder_hidden_states=enc.to(bf16).float(), image_rotary_emb=rope)[0]
+        ref = ob(lat.to(bf16), tb, encoder_hidden_states=enc.to(bf16), image_rotary_emb=rope)[0]
+        got = ours(lat.to(bf16).cuda(), tb.cuda(), encoder_hidden_states=enc.to(bf16).cuda(),
+                   image_rotary_emb=(rope[0].cuda(), rope[1].cuda()), return_dict=False)[0]
+    assert got.shape == (B, C, F, H, W) and got.dtype == bf16
+    three_way(got, ref, truth, name=name)
+
+
+def test_transformer_i2v_inpaint_channels():
+    """predict_i2v path: inpaint_latents (1 mask + 16 masked-video channels) concatenated on channels -> in_channels 33."""
+    from oracle import dit
+    cfg = dict(CFG_TINY, in_channels=33)
+    o32, ob, ours = _build(cfg)
+    B, F, H, W, S_t = 2, 2, 8, 8, 16
+    lat, enc, t = _inputs(B, 16, F, H, W, S_t, cfg["text_embed_dim"])
+    inp = torch.randn(B, 17, F, H, W, generator=torch.Generator().manual_seed(5))
+    rope = dit.rope_for_video(H * 8, W * 8, F)
+    tb = t.to(bf16)
+    with torch.no_grad():
+        truth = o32(lat.to(bf16).float(), tb.float(), encoder_hidden_states=enc.to(bf16).float(), image_rotary_emb=rope,
+                    inpaint_latents=inp.to(bf16).float())[0]
+        ref = ob(lat.to(bf16), tb, encoder_hidden_states=enc.to(bf16), image_rotary_emb=rope, inpaint_latents=inp.to(bf16))[0]
+        got = ours(lat.to(bf16).cuda(), tb.cuda(), encoder_hidden_states=enc.to(bf16).cuda(),
+                   image_rotary_emb=(rope[0].cuda(), rope[1].cuda()), inpaint_latents=inp.to(bf16).cuda())
+    assert got.sample.shape == (B, 16, F, H, W)
+    three_way(got.sample, ref, truth, name="i2v_inpaint")
+
+
+def test_config_surface_and_state_dict_keys():
+    from oracle import dit
+    from easyanimate_b200.transformer3d import EasyAnimateTransformer3DModel
+    m = EasyAnimateTransformer3DModel(**CFG_TINY)
+    assert m.config.in_channels == 16 and m.config.patch_size == 2 and m.config.attention_head_dim == 64
+    assert m.config.get("time_position_encoding_type", "2d_rope") == "3d_rope"
+    assert m.config.get("not_there", 7) == 7 and m.config.enable_text_attention_mask is True
+    assert set(m.state_dict().keys()) == set(dit.OracleTransformer3D(**CFG_TINY).state_dict().keys())
