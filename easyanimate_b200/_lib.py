@@ -90,16 +90,8 @@ class AttnArgs(C.Structure):
 class ConvArgs(C.Structure):
     _fields_ = [
         ("x", vp), ("w", vp), ("bias", vp), ("residual", vp), ("out", vp),
-        ("N", i64), ("T", i64), ("H", i64), ("W", i64), ("Cin", i64), ("Cout", i64),
-        ("upsample", i32), ("out_nchw", i32), ("ldo_c", i64),
-    ]
-
-
-class GnArgs(C.Structure):
-    _fields_ = [
-        ("x", vp), ("y", vp), ("gamma", vp), ("beta", vp), ("stats", vp),
-        ("frames", i64), ("HW", i64), ("C", i64), ("groups", i64),
-        ("eps", f32), ("silu", i32),
+        ("T", i64), ("H", i64), ("W", i64), ("Cin", i64), ("Cout", i64), ("Cout_pad", i64),
+        ("dup_frames", i32), ("out_planar", i32),
     ]
 
 
@@ -124,6 +116,17 @@ ea_unpatchify = _sig("ea_unpatchify", [vp, vp, i64, i64, i64, i64, i64, i64, vp]
 ea_attn_fwd = _sig("ea_attn_fwd", [C.POINTER(AttnArgs), vp])
 ea_transpose_v = _sig("ea_transpose_v", [vp, vp, i64, i64, i64, vp])
 ea_cfg_euler_step = _sig("ea_cfg_euler_step", [vp, vp, vp, vp, i64, f32, i32, f32, f32, vp])
+ea_conv3d_causal = _sig("ea_conv3d_causal", [C.POINTER(ConvArgs), vp])
+ea_vae_prepare_latents = _sig("ea_vae_prepare_latents", [vp, vp, vp, vp, i64, i64, i64, i64, i64, vp])
+ea_groupnorm_workspace = _sig("ea_groupnorm_workspace", [i64, i64], C.c_size_t)
+ea_groupnorm_stats = _sig("ea_groupnorm_stats", [vp, vp, vp, C.c_size_t, i64, i64, i64, i64, f32, vp])
+ea_groupnorm_apply = _sig("ea_groupnorm_apply", [vp, vp, vp, vp, vp, i64, i64, i64, i64, i32, vp])
+ea_upsample2x = _sig("ea_upsample2x", [vp, vp, i64, i64, i64, i64, vp])
+ea_softmax_rows = _sig("ea_softmax_rows", [vp, vp, i64, i64, i64, i64, vp])
+ea_transpose2d = _sig("ea_transpose2d", [vp, vp, i64, i64, i64, i64, vp])
+ea_tile_blend = _sig("ea_tile_blend", [vp, i64, i64, i64, i64, vp, i64, i64, i64, i64, i64, i64, i32, vp])
+ea_copy2d = _sig("ea_copy2d", [vp, i64, i64, vp, i64, i64, i64, i64, i64, vp])
+ea_corner_blend = _sig("ea_corner_blend", [vp, vp, i64, i64, i64, i64, i64, vp])
 
 
 def check(rc: int, what: str = "") -> None:

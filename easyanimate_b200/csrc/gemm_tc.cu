@@ -152,6 +152,7 @@ EA_DEVICE void epilogue_chunk32(const GemmDevArgs& p, int row, int col0, uint32_
 // QKV epilogue for one head (64 columns) of one row.
 EA_DEVICE void epilogue_qkv_head(const GemmDevArgs& p, int row, int col0, uint32_t tmem_row_addr) {
   uint32_t a0[32], a1[32];
+  __syncwarp();  // rows >= M returned early in the previous head
   tmem_ld32(tmem_row_addr, a0);
   tmem_ld32(tmem_row_addr + 32, a1);
   tmem_ld_wait();
@@ -357,6 +358,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t acc[32];
+          __syncwarp();  // reconverge after the masked epilogue of the previous chunk
           tmem_ld32(trow + c * 32, acc);
           tmem_ld_wait();
           if (row < p.M && n0 + c * 32 < p.N) epilogue_chunk32<EPI>(p, row, n0 + c * 32, acc);

@@ -188,6 +188,64 @@ int ea_attn_fwd(const ea_attn_args* args, void* stream);
 /* v[BH,S,64] -> vt[BH,64,S_pad] (columns >= S zero-filled); S_pad % 8 == 0. */
 int ea_transpose_v(const void* v, void* vt, int64_t BH, int64_t S, int64_t S_pad, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * MagViT VAE decode (AutoencoderKLMagvit.decode, autoencoder_magvit.py:271-317,381-448; Decoder,
+ * omnigen_enc_dec.py:555-677).  Activations are channels-last [T,H,W,C] bf16 for one batch element.
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* Whole-sequence causal 3x3x3 convolution (CausalConv3d.forward, vaemodules/common.py:84-141; temporal left
+ * replicate padding 2, spatial zero padding 1) as an implicit GEMM on tcgen05.
+ *   x   [T,H,W,Cin]  bf16, Cin % 64 == 0
+ *   w   [Cout_pad, 27*Cin] bf16, k = ((kt*3+kh)*3+kw)*Cin + ci  (rows >= Cout are zero)
+ *   out [T',H,W,Cout] channels-last, or planar [Cout,T',H,W] when out_planar (conv_out);
+ *       T' = 2T-1 when dup_frames (nearest temporal x2 of every frame but the first, upsamplers.py:146-152), else T
+ *   residual (optional) [T,H,W,Cout]: out = bf16(bf16(conv + bias) + residual)   (ResidualBlock3D, common.py:323) */
+typedef struct {
+  const void* x;
+  const void* w;
+  const void* bias;     /* [Cout] bf16 */
+  const void* residual; /* or NULL */
+  void* out;
+  int64_t T, H, W, Cin, Cout, Cout_pad;
+  int32_t dup_frames;
+  int32_t out_planar;
+} ea_conv3d_args;
+
+int ea_conv3d_causal(const ea_conv3d_args* args, void* stream);
+
+/* post_quant_conv (1x1x1, autoencoder_magvit.py:182,281) fused with NCTHW->THWC: z [C,T,H,W] planar ->
+ * y [T,H,W,Cpad] (channels >= C zero). C <= 32. */
+int ea_vae_prepare_latents(const void* z, const void* w, const void* bias, void* y, int64_t C, int64_t Cpad, int64_t T,
+                           int64_t H, int64_t W, void* stream);
+
+/* Per-frame GroupNorm (common.py:301-319 with set_3dgroupnorm; omnigen_enc_dec.py:603-609):
+ * stats[frames,groups,2] = (mean, rstd) fp32; workspace = ea_groupnorm_workspace() bytes of scratch. */
+size_t ea_groupnorm_workspace(int64_t frames, int64_t groups);
+int ea_groupnorm_stats(const void* x, void* stats, void* workspace, size_t workspace_bytes, int64_t frames, int64_t HW,
+                       int64_t C, int64_t groups, float eps, void* stream);
+/* y = [SiLU](bf16((x-mean)*rstd*gamma+beta)) */
+int ea_groupnorm_apply(const void* x, void* y, const void* gamma, const void* beta, const void* stats, int64_t frames,
+                       int64_t HW, int64_t C, int64_t groups, int32_t silu, void* stream);
+
+/* F.interpolate(scale_factor=(1,2,2), mode="nearest") (upsamplers.py:35,143): [T,H,W,C] -> [T,2H,2W,C] */
+int ea_upsample2x(const void* x, void* y, int64_t T, int64_t H, int64_t W, int64_t C, void* stream);
+
+/* mid-block SpatialAttention helpers (attention_processors.py:118-131): row softmax of fp32 scores -> bf16, and a
+ * 2-D bf16 transpose (V^T as the K-major operand of P·V). */
+int ea_softmax_rows(const void* s, void* p, int64_t M, int64_t N, int64_t lds, int64_t ldp, void* stream);
+int ea_transpose2d(const void* in, void* out, int64_t R, int64_t C, int64_t ldi, int64_t ldo, void* stream);
+
+/* tiled_decode blending (autoencoder_magvit.py:319-337,403-443) on planar [planes][H][W] images:
+ * ea_tile_blend: b[r][c] = a[a_off_r+r][a_off_c+c]*(1-k/extent) + b[r][c]*(k/extent), k = r (axis 0) or c (axis 1)
+ * ea_copy2d: strided crop/concat copy; ea_corner_blend: dst = w*src + (1-w)*dst, w = min(x/(W-1), y/(H-1)). */
+int ea_tile_blend(const void* a, int64_t a_plane, int64_t a_ld, int64_t a_off_r, int64_t a_off_c, void* b,
+                  int64_t b_plane, int64_t b_ld, int64_t planes, int64_t rows, int64_t cols, int64_t extent,
+                  int32_t axis, void* stream);
+int ea_copy2d(const void* src, int64_t s_plane, int64_t s_ld, void* dst, int64_t d_plane, int64_t d_ld, int64_t planes,
+              int64_t rows, int64_t cols, void* stream);
+int ea_corner_blend(const void* src, void* dst, int64_t d_plane, int64_t d_ld, int64_t planes, int64_t Hc, int64_t Wc,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif
