@@ -64,9 +64,37 @@ struct GemmCfg {
 // ------------------------------------------------------------------------------------------------
 // epilogue helpers: one thread owns one accumulator row, `v` holds 32 consecutive columns
 // ------------------------------------------------------------------------------------------------
+// Ragged right edge (N % 32 != 0): same arithmetic as the vector path, one column at a time.
+template <int EPI>
+EA_DEVICE void epilogue_tail(const GemmDevArgs& p, int row, int col0, int nvalid, uint32_t (&acc)[32]) {
+#pragma unroll 1
+  for (int j = 0; j < nvalid; ++j) {
+    const int col = col0 + j;
+    float v = __uint_as_float(acc[j]);
+    if constexpr (EPI == EA_EPI_SCALE_F32) {
+      reinterpret_cast<float*>(p.out)[(int64_t)row * p.ldo + col] = v * p.scale;
+    } else {
+      if (p.bias != nullptr) v += __bfloat162float(p.bias[col]);
+      v = bf16_round(v);
+      if constexpr (EPI == EA_EPI_BIAS_GELU) v = gelu_tanh(v);
+      if constexpr (EPI == EA_EPI_BIAS_GATE_RES) {
+        const int b = row / p.rows_per_batch;
+        const float g = __bfloat162float(p.gate[(int64_t)b * p.gate_stride + col]);
+        v = __bfloat162float(p.residual[(int64_t)row * p.ldr + col]) + bf16_round(g * v);
+      }
+      if constexpr (EPI == EA_EPI_BIAS_RES) v += __bfloat162float(p.residual[(int64_t)row * p.ldr + col]);
+      reinterpret_cast<bf16*>(p.out)[(int64_t)row * p.ldo + col] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
 template <int EPI>
 EA_DEVICE void epilogue_chunk32(const GemmDevArgs& p, int row, int col0, uint32_t (&acc)[32]) {
-  // row < M guaranteed by caller; col0 + 32 <= N guaranteed (N % 32 == 0)
+  // row < M guaranteed by caller
+  if (col0 + 32 > p.N) {
+    epilogue_tail<EPI>(p, row, col0, p.N - col0, acc);
+    return;
+  }
   if constexpr (EPI == EA_EPI_SCALE_F32) {
     float* o = reinterpret_cast<float*>(p.out) + (int64_t)row * p.ldo + col0;
 #pragma unroll
@@ -419,9 +447,9 @@ static int dispatch_bn(const void* a, int64_t lda, const void* w, int64_t ldw, c
   // Wide tiles unless they would leave most SMs idle.
   const int sms = sm_count();
   auto tiles = [&](int bn) { return (int64_t)((p.M + kBM - 1) / kBM) * ((p.N + bn - 1) / bn); };
-  if (p.N % 256 == 0 && tiles(256) >= sms) return launch_gemm<256, EPI>(a, lda, w, ldw, p, stream);
-  if (p.N % 128 == 0 && tiles(128) >= sms / 2) return launch_gemm<128, EPI>(a, lda, w, ldw, p, stream);
-  if (p.N % 128 == 0 && p.N % 64 != 0) return launch_gemm<128, EPI>(a, lda, w, ldw, p, stream);
+  // (ragged N is fine for every width: TMA zero-fills the missing weight rows, the epilogue masks the columns)
+  if (p.N >= 256 && tiles(256) >= sms) return launch_gemm<256, EPI>(a, lda, w, ldw, p, stream);
+  if (p.N >= 128 && tiles(128) >= sms / 2) return launch_gemm<128, EPI>(a, lda, w, ldw, p, stream);
   return launch_gemm<64, EPI>(a, lda, w, ldw, p, stream);
 }
 
@@ -435,7 +463,6 @@ extern "C" int ea_gemm(const ea_gemm_args* g, void* stream_) {
   EA_REQUIRE(g->a && g->w && g->out, "ea_gemm: null pointer");
   EA_REQUIRE(g->M > 0 && g->N > 0 && g->K > 0, "ea_gemm: empty problem");
   EA_REQUIRE(g->M < (1ll << 31) && g->N < (1ll << 31) && g->K < (1ll << 31), "ea_gemm: dims exceed int32");
-  EA_REQUIRE(g->N % 32 == 0, "ea_gemm: N must be a multiple of 32");
   EA_REQUIRE(g->lda % 8 == 0 && g->ldw % 8 == 0, "ea_gemm: lda/ldw must be multiples of 8 (16-byte TMA strides)");
   EA_REQUIRE(g->lda >= g->K && g->ldw >= g->K && g->ldo >= g->N, "ea_gemm: leading dimension too small");
   EA_REQUIRE((reinterpret_cast<uintptr_t>(g->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(g->w) & 15) == 0 &&

@@ -1,0 +1,80 @@
+"""The C-ABI shared library loads without a GPU and exports every symbol include/ea_b200.h declares; host-side
+mirrors of the reference's module surface behave like the reference (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "ea_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ea_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(os.path.join(ROOT, "easyanimate_b200", "libea_b200.so"))
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ea_b200.h but not exported"
+    lib.ea_abi_version.restype = ctypes.c_int
+    assert lib.ea_abi_version() == 1
+    lib.ea_last_error.restype = ctypes.c_char_p
+    assert isinstance(lib.ea_last_error(), bytes)
+
+
+def test_argument_validation_without_gpu():
+    from easyanimate_b200 import _lib as L
+    args = L.GemmArgs()  # all-null
+    assert L.ea_gemm(ctypes.byref(args), None) == -1
+    assert b"null pointer" in L.ea_last_error()
+    a = L.AttnArgs(q=1, k=1, v=1, B=1, H=1, S=8, head_dim=128)
+    assert L.ea_attn_fwd(ctypes.byref(a), None) == -1 and b"head_dim" in L.ea_last_error()
+
+
+def test_ops_refuse_cpu_tensors():
+    from easyanimate_b200 import ops, _lib as L
+    x = torch.zeros(4, 64, dtype=torch.bfloat16)
+    with pytest.raises(L.EaError, match="no CPU path"):
+        ops.gemm(x, x)
+
+
+def test_transformer_config_surface_and_keys():
+    from oracle import dit
+    from easyanimate_b200.transformer3d import EasyAnimateTransformer3DModel
+    cfg = dict(num_attention_heads=2, attention_head_dim=64, in_channels=16, out_channels=16, patch_size=2, num_layers=2,
+               time_embed_dim=64, add_norm_text_encoder=True, text_embed_dim=128, text_embed_dim_t5=None)
+    m = EasyAnimateTransformer3DModel(**cfg)
+    assert m.config.in_channels == 16 and m.config.patch_size == 2 and m.config.attention_head_dim == 64
+    assert m.config.get("time_position_encoding_type", "2d_rope") == "3d_rope"
+    assert m.config.get("not_there", 7) == 7 and m.config.enable_text_attention_mask is True
+    assert m.resize_inpaint_mask_directly is False and m.enable_clip_in_inpaint is True and m.teacache is None
+    assert set(m.state_dict().keys()) == set(dit.OracleTransformer3D(**cfg).state_dict().keys())
+    assert m.to(torch.bfloat16).dtype == torch.bfloat16
+    with pytest.raises(ValueError):
+        EasyAnimateTransformer3DModel(**dict(cfg, attention_head_dim=128))
+
+
+def test_vae_config_surface_and_keys():
+    from oracle import vae
+    from easyanimate_b200.autoencoder_magvit import AutoencoderKLMagvit
+    kw = dict(latent_channels=16, cache_mag_vae=True, spatial_group_norm=True, mid_block_attention_type="spatial",
+              mini_batch_encoder=4, mini_batch_decoder=1, scaling_factor=0.7125, block_out_channels=[64, 64, 128, 128],
+              up_block_types='("SpatialUpBlock3D", "SpatialTemporalUpBlock3D", "SpatialTemporalUpBlock3D", "SpatialTemporalUpBlock3D",)')
+    m = AutoencoderKLMagvit(**kw)
+    assert m.config.scaling_factor == 0.7125 and m.config.latent_channels == 16
+    assert m.config.block_out_channels == [64, 64, 128, 128]
+    assert m.quant_conv.weight.ndim == 5 and m.cache_mag_vae and m.mini_batch_decoder == 1 and m.mini_batch_encoder == 4
+    assert m.tile_latent_min_size == 48
+    ours = {k for k in m.state_dict() if k.startswith("decoder.") or k.startswith("post_quant_conv.")}
+    ref = {k for k in vae.OracleAutoencoderKLMagvit(block_out_channels=(64, 64, 128, 128)).state_dict()}
+    assert ours == ref
+    with pytest.raises(NotImplementedError):
+        AutoencoderKLMagvit(**dict(kw, cache_mag_vae=False))
+    with pytest.raises(NotImplementedError):
+        m.encode(torch.zeros(1))
