@@ -12,6 +12,7 @@ import torch
 from . import _lib as L
 
 bf16 = torch.bfloat16
+ATTN_TIMING = None  # set to a list by bench.py to collect (start, end) CUDA events around every attention launch
 
 
 def _stream() -> int:
@@ -189,5 +190,12 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, S_text: int, *,
     args = L.AttnArgs(q=_p(q), k=_p(k), v=_p(v), out_text=_p(out_text) if S_text else None,
                       out_video=_p(out_video) if S - S_text else None, B=B, H=H, S=S, S_text=S_text, S_pad=S_pad,
                       head_dim=64, scale=scale, variant=variant)
+    timing = ATTN_TIMING
+    if timing is not None:  # bench.py: per-launch CUDA events on the launching stream for the roofline line
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     L.check(L.ea_attn_fwd(C.byref(args), _stream()), "ea_attn_fwd")
+    if timing is not None:
+        e1.record()
+        timing.append((e0, e1))
     return out_text, out_video

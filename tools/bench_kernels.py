@@ -63,7 +63,53 @@ def bench_attn():
         print(json.dumps(res), flush=True)
 
 
+def vae_conv_flops(F_lat, h, w, boc=(128, 256, 512, 512), mid_attn=True):
+    """conv FLOPs of one untiled decode (BASELINE.md §2 / §4 tracer closed form for the released architecture)."""
+    T1, T2, T3 = F_lat, 2 * F_lat - 1, 4 * F_lat - 3
+    c0, c1, c2, c3 = boc  # 128,256,512,512
+    def conv(T, H, W, cin, cout, k=27): return 2.0 * T * H * W * cout * cin * k
+    fl = conv(T1, h, w, 16, c3)                                  # conv_in
+    fl += 4 * conv(T1, h, w, c3, c3)                             # mid block: 2 res blocks
+    fl += 6 * conv(T1, h, w, c3, c3) + conv(T1, 2 * h, 2 * w, c3, c3)          # up0 + spatial upsampler
+    fl += 6 * conv(T1, 2 * h, 2 * w, c3, c3) + conv(T1, 4 * h, 4 * w, c3, c3)  # up1 (+temporal x2 after conv)
+    fl += conv(T2, 4 * h, 4 * w, c3, c1) + 5 * conv(T2, 4 * h, 4 * w, c1, c1) + conv(T2, 4 * h, 4 * w, c3, c1, 1)
+    fl += conv(T2, 8 * h, 8 * w, c1, c1)                         # up2 upsampler
+    fl += conv(T3, 8 * h, 8 * w, c1, c0) + 5 * conv(T3, 8 * h, 8 * w, c0, c0) + conv(T3, 8 * h, 8 * w, c1, c0, 1)
+    fl += conv(T3, 8 * h, 8 * w, c0, 3)                          # conv_out
+    return fl
+
+
+def bench_vae():
+    from easyanimate_b200.autoencoder_magvit import AutoencoderKLMagvit
+    shapes = [(13, 48, 48, False), (13, 64, 64, False), (13, 90, 160, False), (13, 90, 160, True)]
+    only = os.environ.get("EA_VAE_SHAPES")
+    with torch.device("cuda"):
+        vae = AutoencoderKLMagvit(latent_channels=16, cache_mag_vae=True, spatial_group_norm=True, mid_block_attention_type="spatial",
+                                  mini_batch_decoder=1, scaling_factor=0.7125).to(bf16)
+    with torch.no_grad():
+        for n, p in vae.named_parameters():
+            if p.dim() >= 2:
+                p.normal_(0, (1.0 / p[0].numel()) ** 0.5)
+            elif "norm" in n and n.endswith("weight"):
+                p.normal_(1.0, 0.05)
+            else:
+                p.normal_(0, 0.05)
+    for F_lat, h, w, tiled in shapes:
+        if only and f"{h}x{w}" not in only:
+            continue
+        vae.use_tiling = tiled
+        z = torch.randn(1, 16, F_lat, h, w, device="cuda").to(bf16)
+        out = vae.decode(z).sample
+        torch.cuda.synchronize()
+        med, best = timeit(lambda: vae.decode(z), reps=3, warmup=1, flush=False)
+        mpix = out.shape[2] * out.shape[3] * out.shape[4] / 1e6
+        fl = vae_conv_flops(F_lat, h, w)
+        print(json.dumps({"kernel": "vae_decode", "z": [1, 16, F_lat, h, w], "tiled": tiled, "frames": out.shape[2], "ms": round(med, 2),
+                          "mpix_per_s": round(mpix / med * 1e3, 1), "untiled_conv_tflop": round(fl / 1e12, 1),
+                          "conv_tflops_if_untiled": round(fl / med / 1e9, 1), "finite": bool(torch.isfinite(out).all())}), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "gemm"
-    {"gemm": bench_gemm, "attn": bench_attn}[which]()
+    {"gemm": bench_gemm, "attn": bench_attn, "vae": bench_vae}[which]()
 
