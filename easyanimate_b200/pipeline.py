@@ -73,8 +73,10 @@ class EasyAnimateSampler:
     """Denoise loop + VAE decode on device-resident tensors, with an optional host-buffer entry point."""
 
     def __init__(self, transformer, vae=None, scheduler: Optional[FlowMatchEulerDiscreteScheduler] = None,
-                 guidance_scale: float = 6.0, cfg_group=None):
+                 guidance_scale: float = 6.0, cfg_group=None, euler_fn=None):
         self.transformer = transformer
+        # CFG combine + Euler update kernel; injectable so the multi-rank host logic can be unit-tested on CPU (gloo)
+        self._euler = euler_fn or ops.cfg_euler_step
         self.vae = vae
         self.scheduler = scheduler or FlowMatchEulerDiscreteScheduler()
         self.guidance_scale = guidance_scale
@@ -100,7 +102,7 @@ class EasyAnimateSampler:
             t_expand = t.reshape(1).expand(B).to(device=latents.device, dtype=bf16)
             pred = self.transformer(latents, t_expand, encoder_hidden_states=embeds, image_rotary_emb=rope,
                                     inpaint_latents=inpaint_latents, return_dict=False)[0]
-            return ops.cfg_euler_step(pred, latents, 1.0, sigma, sigma_next, use_cfg=False)
+            return self._euler(pred, latents, 1.0, sigma, sigma_next, use_cfg=False)
         if self.cfg_group is None:
             latent_in = torch.cat([latents] * 2)
             inp = None if inpaint_latents is None else torch.cat([inpaint_latents] * 2)
@@ -115,7 +117,7 @@ class EasyAnimateSampler:
                                     image_rotary_emb=rope, inpaint_latents=inpaint_latents, return_dict=False)[0]
             pred = torch.empty((2 * B,) + tuple(mine.shape[1:]), device=mine.device, dtype=mine.dtype)
             dist.all_gather_into_tensor(pred, mine.contiguous(), group=self.cfg_group)
-        return ops.cfg_euler_step(pred, latents, self.guidance_scale, sigma, sigma_next, use_cfg=True)
+        return self._euler(pred, latents, self.guidance_scale, sigma, sigma_next, use_cfg=True)
 
     def step_from_host(self, latents_host: torch.Tensor, i: int, embeds_host: torch.Tensor, rope,
                        out_host: Optional[torch.Tensor] = None, device="cuda") -> torch.Tensor:
