@@ -41,7 +41,10 @@ def bench_gemm():
 def bench_attn():
     from easyanimate_b200 import ops
     variant = int(os.environ.get("EA_ATTN_VARIANT", "0"))
-    for (B, H, S, St) in [(1, 48, 13312 + 256, 256), (1, 48, 47056, 256)]:
+    shapes = [(1, 48, 13312 + 256, 256), (1, 48, 47056, 256)]
+    if os.environ.get("EA_ATTN_SMALL"):
+        shapes = [(1, 16, 8192 + 256, 256)]
+    for (B, H, S, St) in shapes:
         q = torch.randn(B, H, S, 64, device="cuda").to(bf16)
         k = torch.randn(B, H, S, 64, device="cuda").to(bf16)
         v = torch.randn(B, H, S, 64, device="cuda").to(bf16)
