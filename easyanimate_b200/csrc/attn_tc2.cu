@@ -1,0 +1,375 @@
+// Joint text+video attention forward, second generation: TWO 128-row query tiles per CTA, ping-ponged.
+//
+//   warps 0-3  : softmax of tile A  (one query row per thread)
+//   warps 4-7  : softmax of tile B
+//   warp  8    : TMA producer (Q once as one 256-row box, K_j / V_j 128-key tiles through 4-stage rings)
+//   warp  9    : MMA issuer: S_t = Q_t K_j^T (TMEM), O_t += P_t V_j with P_t read from TMEM where it ALIASES S_t
+//   warp 10    : TMEM allocator
+//
+// While the softmax warps of one tile run, the tensor pipe computes the other tile's QK^T / PV, and both tiles share
+// every K/V shared-memory stage (half the TMA/L2 traffic per FLOP of the one-tile kernel in attn_tc.cu).
+// The softmax never holds a score row in registers: pass 1 streams S from TMEM for the row max, pass 2 streams it
+// again, exponentiates, and stores bf16 P back over the columns it has already consumed.
+// head_dim 64 is exp-bound on Blackwell (16 ex2/clk/SM vs 8192 MACs/clk/SM): POLY of every 8 exponentials are
+// evaluated on the FMA pipe instead (Cody-Waite range reduction + degree-3 minimax polynomial, rel. err 1e-4, below
+// the 2e-3 rounding of P to bf16).
+#include "common.cuh"
+#include "host.h"
+#include "../../include/ea_b200.h"
+
+namespace ea {
+
+extern void count_launch();
+
+namespace a2 {
+
+constexpr int kThreads = 384;
+constexpr int kQT = 128;
+constexpr int kKT = 128;
+constexpr int kHD = 64;
+constexpr int kStages = 4;
+
+struct Args {
+  bf16* out_text;
+  bf16* out_video;
+  int B, H, S, S_text;
+  float scale_log2;
+};
+
+struct Smem {
+  static constexpr int kQBytes = 2 * kQT * kHD * 2;  // 32 KB (tile A | tile B)
+  static constexpr int kKBytes = kKT * kHD * 2;
+  static constexpr int kVBytes = kKT * kHD * 2;
+  static constexpr int kOffQ = 0;
+  static constexpr int kOffK = kOffQ + kQBytes;
+  static constexpr int kOffV = kOffK + kStages * kKBytes;
+  static constexpr int kOffBar = kOffV + kStages * kVBytes;
+  static constexpr int kTotal = kOffBar + 256 + 1024;
+};
+
+EA_DEVICE void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+EA_DEVICE float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// 2^x for x <= 0 on the FMA/ALU pipes. round-to-nearest split x = n + f, f in [-0.5, 0.5]; 2^f by a degree-3 minimax
+// polynomial; 2^n by adding n to the exponent field.
+EA_DEVICE float exp2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float y = x + 12582912.0f;  // 1.5 * 2^23: the integer part of x lands in the low mantissa bits
+  const float n = y - 12582912.0f;
+  const float f = x - n;
+  float p = 0.05500892f;
+  p = fmaf(p, f, 0.24221097f);
+  p = fmaf(p, f, 0.69328290f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(y) << 23));
+}
+
+template <int POLY>
+__global__ void __launch_bounds__(kThreads, 1)
+attn2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+             const __grid_constant__ CUtensorMap tmap_v, const Args p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + Smem::kOffQ;
+  uint8_t* sK = smem + Smem::kOffK;
+  uint8_t* sV = smem + Smem::kOffV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::kOffBar);
+  uint64_t* q_full = bars;                  // 1
+  uint64_t* k_full = bars + 1;              // kStages
+  uint64_t* k_empty = k_full + kStages;
+  uint64_t* v_full = k_empty + kStages;
+  uint64_t* v_empty = v_full + kStages;
+  uint64_t* s_full = v_empty + kStages;     // [2] per tile
+  uint64_t* p_ready = s_full + 2;           // [2]
+  uint64_t* o_done = p_ready + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (2 * kQT);
+  const int bh = blockIdx.y;
+  const int nblk = (p.S + kKT - 1) / kKT;
+
+  // TMEM columns: tile t: S_t = [128 t, 128 t + 128) with P_t aliasing its first 64 columns; O_t = [256 + 64 t, +64)
+  constexpr uint32_t kColO = 256;
+  constexpr uint32_t kTmemCols = 512;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], 128);
+      mbar_init(&o_done[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 10) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      mbar_arrive_expect_tx(q_full, Smem::kQBytes);
+      tma_load_3d(sQ, &tmap_q, q_full, 0, q0, bh);  // one 256-row box: tile A then tile B
+      int st = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], Smem::kKBytes);
+        tma_load_3d(sK + st * Smem::kKBytes, &tmap_k, &k_full[st], 0, j * kKT, bh);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], Smem::kVBytes);
+        tma_load_3d(sV + st * Smem::kVBytes, &tmap_v, &v_full[st], 0, j * kKT, bh);
+        if (++st == kStages) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(kQT, kKT, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(kQT, kHD, 0, 1);  // V is the MN-major B operand
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      auto issue_qk = [&](int t, int j) {
+        const int st = j % kStages;
+        const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ + t * (kQT * kHD * 2)));
+        const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + st * Smem::kKBytes));
+        const uint32_t d = tmem_base + t * kKT;
+#pragma unroll
+        for (int k = 0; k < kHD / 16; ++k) umma_ss(d, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+        umma_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int t, int j) {
+        const int st = j % kStages;
+        const uint32_t vaddr = smem_u32(sV + st * Smem::kVBytes);
+        const uint32_t d = tmem_base + kColO + t * kHD;
+        const uint32_t pa = tmem_base + t * kKT;  // bf16 P: 64 packed columns over the start of S_t
+#pragma unroll
+        for (int k = 0; k < kKT / 16; ++k)
+          umma_ts(d, pa + k * 8, umma_desc_sw128_mn(vaddr + k * 2048, 16384, 1024), idesc_pv, (j | k) != 0);
+        umma_commit(&o_done[t]);
+      };
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      issue_qk(1, 0);
+      umma_commit(&k_empty[0]);
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j % kStages;
+        const uint32_t par = j & 1;
+        const bool more = j + 1 < nblk;
+        // tile A
+        mbar_wait(&p_ready[0], par);
+        mbar_wait(&v_full[st], (j / kStages) & 1);
+        tc_fence_after();
+        issue_pv(0, j);
+        if (more) {
+          mbar_wait(&k_full[(j + 1) % kStages], ((j + 1) / kStages) & 1);
+          tc_fence_after();
+          issue_qk(0, j + 1);
+        }
+        // tile B
+        mbar_wait(&p_ready[1], par);
+        tc_fence_after();
+        issue_pv(1, j);
+        umma_commit(&v_empty[st]);
+        if (more) {
+          issue_qk(1, j + 1);
+          umma_commit(&k_empty[(j + 1) % kStages]);
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ===== softmax / correction / epilogue: tile t, one query row per thread =====
+    const int t = warp >> 2;
+    const int ew = warp & 3;
+    const int r = ew * 32 + lane;
+    const uint32_t lane_off = uint32_t(ew * 32) << 16;
+    const uint32_t tS = tmem_base + lane_off + t * kKT;
+    const uint32_t tO = tmem_base + lane_off + kColO + t * kHD;
+    float m_ref = -INFINITY;  // reference max in scaled log2 units
+    float l = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      const int valid = p.S - j * kKT;  // >= 128 except in the last block (TMA zero-filled the missing keys)
+      // ---- pass 1: row max of the raw scores
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tS + c * 32, v);
+        tmem_ld_wait();
+        if (valid >= kKT) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+      mx *= p.scale_log2;
+      if (j == 0) {
+        m_ref = mx;
+      } else {
+        const bool grow = mx > m_ref + 8.0f;
+        if (__any_sync(0xffffffffu, grow)) {
+          mbar_wait(&o_done[t], (j - 1) & 1);  // PV_{j-1} of this tile has landed in O_t
+          tc_fence_after();
+          const float m_new = grow ? mx : m_ref;
+          const float f = ex2(m_ref - m_new);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tO + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+            tmem_st32(tO + c * 32, v);
+          }
+          tmem_st_wait();
+          l *= f;
+          m_ref = m_new;
+        }
+      }
+      // ---- pass 2: p = 2^(s*c - m_ref), row sum, bf16 P written over the consumed part of S
+      float sum = 0.f;
+      const float neg_m = -m_ref;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tS + c * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float x0 = fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m);
+          float x1 = fmaf(__uint_as_float(v[i + 1]), p.scale_log2, neg_m);
+          float e0 = ((i & 7) < POLY) ? exp2_poly(x0) : ex2(x0);
+          float e1 = (((i + 1) & 7) < POLY) ? exp2_poly(x1) : ex2(x1);
+          if (valid < kKT) {
+            if (c * 32 + i >= valid) e0 = 0.f;
+            if (c * 32 + i + 1 >= valid) e1 = 0.f;
+          }
+          sum += e0 + e1;
+          pk[i >> 1] = pack_bf16x2(e0, e1);
+        }
+        tmem_st16(tS + c * 16, pk);
+      }
+      l += sum;
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_ready[t]);
+    }
+    // ---- epilogue: O_t / l -> token-major bf16
+    mbar_wait(&o_done[t], (nblk - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    const int srow = q0 + t * kQT + r;
+    bf16* dst = nullptr;
+    if (srow < p.S) {
+      const int b = bh / p.H, h = bh % p.H;
+      const int64_t d = (int64_t)p.H * kHD;
+      if (srow < p.S_text)
+        dst = p.out_text + ((int64_t)b * p.S_text + srow) * d + h * kHD;
+      else
+        dst = p.out_video + ((int64_t)b * (p.S - p.S_text) + (srow - p.S_text)) * d + h * kHD;
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      __syncwarp();
+      tmem_ld32(tO + c * 32, v);
+      tmem_ld_wait();
+      if (dst != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(v[i * 8 + 0]) * inv_l, __uint_as_float(v[i * 8 + 1]) * inv_l);
+          w.y = pack_bf16x2(__uint_as_float(v[i * 8 + 2]) * inv_l, __uint_as_float(v[i * 8 + 3]) * inv_l);
+          w.z = pack_bf16x2(__uint_as_float(v[i * 8 + 4]) * inv_l, __uint_as_float(v[i * 8 + 5]) * inv_l);
+          w.w = pack_bf16x2(__uint_as_float(v[i * 8 + 6]) * inv_l, __uint_as_float(v[i * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + c * 32 + i * 8) = w;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <int POLY>
+static int launch(const ea_attn_args* g, cudaStream_t stream) {
+  const int64_t BH = g->B * g->H;
+  CUtensorMap tq, tk, tv;
+  uint64_t dims[3] = {(uint64_t)kHD, (uint64_t)g->S, (uint64_t)BH};
+  uint64_t strides[2] = {(uint64_t)kHD * 2, (uint64_t)g->S * kHD * 2};
+  uint32_t box_q[3] = {kHD, 2 * kQT, 1};
+  uint32_t box_kv[3] = {kHD, kKT, 1};
+  int rc = make_tmap_bf16(&tq, g->q, 3, dims, strides, box_q, true);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tk, g->k, 3, dims, strides, box_kv, true);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tv, g->v, 3, dims, strides, box_kv, true);
+  if (rc) return rc;
+  Args p{};
+  p.out_text = reinterpret_cast<bf16*>(g->out_text);
+  p.out_video = reinterpret_cast<bf16*>(g->out_video);
+  p.B = (int)g->B; p.H = (int)g->H; p.S = (int)g->S; p.S_text = (int)g->S_text;
+  p.scale_log2 = g->scale * 1.4426950408889634f;
+  auto kern = attn2_kernel<POLY>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kTotal);
+    if (e != cudaSuccess) return fail(EA_ERR_CUDA, std::string("cudaFuncSetAttribute(attn2): ") + cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((g->S + 2 * kQT - 1) / (2 * kQT)), (unsigned)BH);
+  kern<<<grid, kThreads, Smem::kTotal, stream>>>(tq, tk, tv, p);
+  count_launch();
+  return check_launch("attn2_kernel");
+}
+
+}  // namespace a2
+
+int launch_attn2(const ea_attn_args* g, int poly, cudaStream_t stream) {
+  switch (poly) {
+    case 0: return a2::launch<0>(g, stream);
+    case 2: return a2::launch<2>(g, stream);
+    case 3: return a2::launch<3>(g, stream);
+    case 4: return a2::launch<4>(g, stream);
+    case 5: return a2::launch<5>(g, stream);
+    default: return fail(EA_ERR_INVALID, "ea_attn_fwd: unsupported polynomial fraction (0,2,3,4,5 of every 8)");
+  }
+}
+
+}  // namespace ea

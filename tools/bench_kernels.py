@@ -40,7 +40,8 @@ def bench_gemm():
 
 def bench_attn():
     from easyanimate_b200 import ops
-    variant = int(os.environ.get("EA_ATTN_VARIANT", "0"))
+    variant = int(os.environ.get("EA_ATTN_VARIANT", "1"), 0)
+    compare = not os.environ.get("EA_ATTN_NO_COMPARE")
     shapes = [(1, 48, 13312 + 256, 256), (1, 48, 47056, 256)]
     if os.environ.get("EA_ATTN_SMALL"):
         shapes = [(1, 16, 8192 + 256, 256)]
@@ -51,6 +52,9 @@ def bench_attn():
         fl = 4.0 * B * H * S * S * 64
         med, best = timeit(lambda: ops.attention(q, k, v, St, variant=variant), reps=5, warmup=2)
         res = {"kernel": "attn_fwd", "variant": variant, "B": B, "H": H, "S": S, "ms": round(med, 3), "tflops": round(fl / med / 1e9, 1)}
+        if not compare:
+            print(json.dumps(res), flush=True)
+            continue
         try:
             medt, _ = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v), reps=5, warmup=2)
             res.update({"torch_sdpa_ms": round(medt, 3), "torch_sdpa_tflops": round(fl / medt / 1e9, 1)})
