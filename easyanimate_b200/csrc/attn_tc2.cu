@@ -217,22 +217,27 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
       tc_fence_after();
       const int valid = p.S - j * kKT;  // >= 128 except in the last block (TMA zero-filled the missing keys)
       // ---- pass 1: row max of the raw scores
-      float mx = -INFINITY;
+      //      (four independent reduction chains; the next chunk's TMEM load is in flight while this one is reduced)
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      uint32_t va[32], vb[32];
+      tmem_ld32(tS, va);
+      tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tS + c * 32, v);
-        tmem_ld_wait();
+        uint32_t(&cur)[32] = (c & 1) ? vb : va;
+        uint32_t(&nxt)[32] = (c & 1) ? va : vb;
+        if (c < 3) tmem_ld32(tS + (c + 1) * 32, nxt);
         if (valid >= kKT) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(cur[i]));
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+            if (c * 32 + i < valid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(cur[i]));
         }
+        if (c < 3) tmem_ld_wait();
       }
-      mx *= p.scale_log2;
+      float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
       if (j == 0) {
         m_ref = mx;
       } else {
@@ -257,30 +262,33 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         }
       }
       // ---- pass 2: p = 2^(s*c - m_ref), row sum, bf16 P written over the consumed part of S
-      float sum = 0.f;
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
       const float neg_m = -m_ref;
+      tmem_ld32(tS, va);
+      tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tS + c * 32, v);
-        tmem_ld_wait();
+        uint32_t(&cur)[32] = (c & 1) ? vb : va;
+        uint32_t(&nxt)[32] = (c & 1) ? va : vb;
+        if (c < 3) tmem_ld32(tS + (c + 1) * 32, nxt);
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float x0 = fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m);
-          float x1 = fmaf(__uint_as_float(v[i + 1]), p.scale_log2, neg_m);
+          float x0 = fmaf(__uint_as_float(cur[i]), p.scale_log2, neg_m);
+          float x1 = fmaf(__uint_as_float(cur[i + 1]), p.scale_log2, neg_m);
           float e0 = ((i & 7) < POLY) ? exp2_poly(x0) : ex2(x0);
           float e1 = (((i + 1) & 7) < POLY) ? exp2_poly(x1) : ex2(x1);
           if (valid < kKT) {
             if (c * 32 + i >= valid) e0 = 0.f;
             if (c * 32 + i + 1 >= valid) e1 = 0.f;
           }
-          sum += e0 + e1;
+          s4[(i >> 1) & 3] += e0 + e1;
           pk[i >> 1] = pack_bf16x2(e0, e1);
         }
+        if (c < 3) tmem_ld_wait();  // chunk c+1 (columns >= 32(c+1)) is in registers before P overwrites [16c,16c+16)
         tmem_st16(tS + c * 16, pk);
       }
-      l += sum;
+      l += (s4[0] + s4[1]) + (s4[2] + s4[3]);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_ready[t]);

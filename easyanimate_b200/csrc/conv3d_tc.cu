@@ -12,6 +12,8 @@
 // zero padding is TMA out-of-bounds fill, causal replicate padding is the coordinate clamp; nothing is gathered or
 // materialised.  Weights are pre-arranged [Cout, 27*Cin] (tap-major K).  MMA/TMEM/epilogue structure as gemm_tc.cu.
 // Fused in the epilogue: bias, residual add, nearest temporal x2 duplication (frames >= 1), planar NCTHW store.
+// MT = number of 128-pixel sub-tiles one CTA accumulates against the same weight tile (2 => 256x BN CTA tile: the
+// kernel is L2->SM bandwidth bound at 128x128 (64 FLOP/B, ncu: 14.2 TB/s xbar), 256x128 moves 85 FLOP/B).
 #include "common.cuh"
 #include "host.h"
 #include "../../include/ea_b200.h"
@@ -37,21 +39,23 @@ struct ConvDevArgs {
   int T_out;
 };
 
-template <int BN>
+template <int BN, int MT>
 struct ConvCfg {
-  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int kABytes = kCM * kCK * 2;
+  static constexpr int kABytes = MT * kCM * kCK * 2;
   static constexpr int kBBytes = BN * kCK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kAccCols = MT * BN;                       // one accumulator stage
+  static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;  // power of two for the shapes used
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static_assert(kTmemCols <= 512, "accumulators exceed TMEM");
 };
 
-template <int BN>
+template <int BN, int MT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const ConvDevArgs p) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, MT>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -94,7 +98,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     int r = tile / p.tiles_n;
     w0 = (r % p.tiles_w) * p.TW;
     r /= p.tiles_w;
-    h0 = (r % p.tiles_h) * p.TH;
+    h0 = (r % p.tiles_h) * (MT * p.TH);
     t = r / p.tiles_h;
   };
 
@@ -132,14 +136,18 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BN;
+        const uint32_t tmem_d = tmem_base + as * Cfg::kAccCols;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
 #pragma unroll
-          for (int k = 0; k < kCK / 16; ++k) umma_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          for (int m = 0; m < MT; ++m) {
+            const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes + m * (kCM * kCK * 2)));
+#pragma unroll
+            for (int k = 0; k < kCK / 16; ++k)
+              umma_ss(tmem_d + m * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
           umma_commit(&empty_bar[stage]);
           if (kb == num_k_blocks - 1) umma_commit(&tfull_bar[as]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -159,13 +167,15 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       decode_tile(tile, t, h0, w0, n0);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const int h = h0 + ph, w = w0 + pw;
-      const bool pix_ok = h < p.H && w < p.W;
-      const uint32_t trow = tmem_base + (uint32_t(ew * 32) << 16) + as * BN;
       const int t_out = p.dup_frames ? (t == 0 ? 0 : 2 * t - 1) : t;
       const int ncopies = (p.dup_frames && t > 0) ? 2 : 1;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int cc = 0; cc < MT * (BN / 32); ++cc) {
+      const int m = cc / (BN / 32), c = cc % (BN / 32);
+      const int h = h0 + m * p.TH + ph, w = w0 + pw;
+      const bool pix_ok = h < p.H && w < p.W;
+      const uint32_t trow = tmem_base + (uint32_t(ew * 32) << 16) + as * Cfg::kAccCols + m * BN;
+      {
         uint32_t acc[32];
         __syncwarp();  // threads may have diverged on pix_ok / channel bounds in the previous chunk
         tmem_ld32(trow + c * 32, acc);
@@ -224,6 +234,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           for (int j = 0; j < 4; ++j) op[j] = o[j];
         }
       }
+      }
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
     }
@@ -237,17 +248,18 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   }
 }
 
-template <int BN>
+template <int BN, int MT>
 static int launch_conv(const ea_conv3d_args* g, cudaStream_t stream) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, MT>;
   ConvDevArgs p{};
   p.T = (int)g->T; p.H = (int)g->H; p.W = (int)g->W; p.Cin = (int)g->Cin; p.Cout = (int)g->Cout;
   // tile shape: 8x16 or 4x32 pixels, whichever wastes fewer out-of-range pixels
   auto waste = [&](int th, int tw) {
+    th *= MT;
     return (int64_t)((p.H + th - 1) / th) * th * ((p.W + tw - 1) / tw) * tw;
   };
   if (waste(4, 32) < waste(8, 16)) { p.TH = 4; p.TW = 32; } else { p.TH = 8; p.TW = 16; }
-  p.tiles_h = (p.H + p.TH - 1) / p.TH;
+  p.tiles_h = (p.H + MT * p.TH - 1) / (MT * p.TH);
   p.tiles_w = (p.W + p.TW - 1) / p.TW;
   p.tiles_n = (int)((g->Cout_pad + BN - 1) / BN);
   p.kt_taps = 3;
@@ -262,7 +274,7 @@ static int launch_conv(const ea_conv3d_args* g, cudaStream_t stream) {
   {
     uint64_t dims[4] = {(uint64_t)g->Cin, (uint64_t)g->W, (uint64_t)g->H, (uint64_t)g->T};
     uint64_t strides[3] = {(uint64_t)g->Cin * 2, (uint64_t)g->W * g->Cin * 2, (uint64_t)g->H * g->W * g->Cin * 2};
-    uint32_t box[4] = {kCK, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+    uint32_t box[4] = {kCK, (uint32_t)p.TW, (uint32_t)(MT * p.TH), 1};  // MT sub-tiles stacked along H
     int rc = make_tmap_bf16(&tx, g->x, 4, dims, strides, box, true);
     if (rc) return rc;
   }
@@ -274,7 +286,7 @@ static int launch_conv(const ea_conv3d_args* g, cudaStream_t stream) {
     int rc = make_tmap_bf16(&tw, g->w, 2, dims, strides, box, true);
     if (rc) return rc;
   }
-  auto kern = conv3d_tc_kernel<BN>;
+  auto kern = conv3d_tc_kernel<BN, MT>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -303,8 +315,11 @@ extern "C" int ea_conv3d_causal(const ea_conv3d_args* g, void* stream_) {
   EA_REQUIRE(g->out_planar || g->Cout % 32 == 0, "ea_conv3d_causal: channels-last output needs Cout % 32 == 0");
   EA_REQUIRE(!(g->out_planar && g->residual), "ea_conv3d_causal: planar output cannot take a residual");
   EA_REQUIRE(g->W < 32768 && g->H < 32768, "ea_conv3d_causal: frame too large");
-  if (g->Cout_pad % 256 == 0) return launch_conv<256>(g, stream);
-  if (g->Cout_pad % 128 == 0) return launch_conv<128>(g, stream);
-  if (g->Cout_pad % 64 == 0) return launch_conv<64>(g, stream);
-  return launch_conv<32>(g, stream);
+  // 256-pixel CTA tiles against a <=128-wide weight tile (TMEM: 2 stages x 2 sub-tiles x 128 columns) unless the
+  // frame is too small to fill the SMs with them.
+  const int64_t tiles256 = g->T * ((g->H + 15) / 16) * ((g->W + 15) / 16) * ((g->Cout_pad + 127) / 128);
+  const bool big = tiles256 >= 2 * sm_count() && !(g->variant & 1);
+  if (g->Cout_pad % 128 == 0) return big ? launch_conv<128, 2>(g, stream) : launch_conv<128, 1>(g, stream);
+  if (g->Cout_pad % 64 == 0) return big ? launch_conv<64, 2>(g, stream) : launch_conv<64, 1>(g, stream);
+  return big ? launch_conv<32, 2>(g, stream) : launch_conv<32, 1>(g, stream);
 }

@@ -3,12 +3,15 @@ channels-last ``[T,H,W,C]`` bf16 tensors for one batch element; torch only alloc
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
 
 from . import _lib as L
 from .ops import _p, _req, _stream, bf16, gemm
+
+CONV_VARIANT = int(os.environ.get("EA_CONV_VARIANT", "0"), 0)  # bit0: force 128-pixel CTA tiles (A/B measurements)
 
 
 def conv3d_causal(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, cout: int, *,
@@ -24,7 +27,7 @@ def conv3d_causal(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, c
         assert residual.shape == (T, H, W, cout) and residual.is_contiguous()
     args = L.ConvArgs(x=_p(x), w=_p(w_packed), bias=_p(bias), residual=_p(residual), out=_p(out), T=T, H=H, W=W,
                       Cin=Cin, Cout=cout, Cout_pad=w_packed.shape[0], dup_frames=int(dup_frames),
-                      out_planar=int(out_planar))
+                      out_planar=int(out_planar), variant=CONV_VARIANT)
     L.check(L.ea_conv3d_causal(C.byref(args), _stream()), "ea_conv3d_causal")
     return out
 

@@ -170,8 +170,10 @@ int ea_cfg_euler_step(const void* pred_uncond, const void* pred_text, const void
  * Replaces F.scaled_dot_product_attention + transpose/reshape/split at processor.py:287-303.
  * q,k,v: [B,H,S,64] bf16 contiguous.  Output is token-major and split at S_text:
  * out_text[B,S_text,H*64], out_video[B,S-S_text,H*64].
- * variant bit0: P operand through TMEM instead of shared memory; bit1: v is pre-transposed [B,H,64,S_pad]
- * (see ea_transpose_v). variant 0 is the default path. */
+ * variant: bit2 set (the default used by the Python layer: 0x34) = two-query-tile ping-pong kernel, bits 4-6 = how
+ * many of every 8 exponentials are evaluated by a polynomial on the FMA pipe instead of MUFU (0,2,3,4,5).
+ * bit2 clear = first-generation one-tile kernel: bit0 P operand through TMEM instead of shared memory; bit1 v is
+ * pre-transposed [B,H,64,S_pad] (see ea_transpose_v). */
 typedef struct {
   const void* q;
   const void* k;
@@ -209,6 +211,7 @@ typedef struct {
   int64_t T, H, W, Cin, Cout, Cout_pad;
   int32_t dup_frames;
   int32_t out_planar;
+  int32_t variant;      /* 0 = default tiling; bit0: force 128-pixel CTA tiles (A/B measurements) */
 } ea_conv3d_args;
 
 int ea_conv3d_causal(const ea_conv3d_args* args, void* stream);
