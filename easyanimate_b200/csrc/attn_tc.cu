@@ -361,6 +361,7 @@ static int launch_attn(const ea_attn_args* g, cudaStream_t stream) {
 namespace ea {
 int launch_attn2(const ea_attn_args* g, int poly, cudaStream_t stream);
 int launch_attn3(const ea_attn_args* g, int poly, cudaStream_t stream);
+int launch_attn4(const ea_attn_args* g, int poly, cudaStream_t stream);
 }
 using namespace ea;
 
@@ -373,6 +374,7 @@ extern "C" int ea_attn_fwd(const ea_attn_args* g, void* stream_) {
   EA_REQUIRE(g->S_text == 0 || g->out_text, "ea_attn_fwd: out_text missing");
   EA_REQUIRE(g->S_text == g->S || g->out_video, "ea_attn_fwd: out_video missing");
   EA_REQUIRE(g->B * g->H <= 65535, "ea_attn_fwd: B*H exceeds grid.y");
+  if ((g->variant & 12) == 12) return ea::launch_attn4(g, (g->variant >> 4) & 7, stream);  // one-pass two-tile kernel
   if (g->variant & 8) return ea::launch_attn3(g, (g->variant >> 4) & 7, stream);  // two tiles, double-buffered S
   if (g->variant & 4) return ea::launch_attn2(g, (g->variant >> 4) & 7, stream);  // two-tile ping-pong kernel
   const bool vt = (g->variant & 2) != 0, pt = (g->variant & 1) != 0;

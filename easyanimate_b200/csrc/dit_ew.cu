@@ -475,3 +475,58 @@ extern "C" int ea_cfg_euler_step(const void* pred_uncond, const void* pred_text,
   count_launch();
   return check_launch("cfg_euler_kernel");
 }
+
+// ---- TeaCache support (transformer3d.py:90-121,1563-1636): relative-L1 change of the block-0 modulated input and
+//      the cached-residual add/sub, kept on the device (the reference round-trips both tensors through the CPU).
+namespace ea {
+__global__ void __launch_bounds__(256) l1_sums_kernel(const bf16* __restrict__ cur, const bf16* __restrict__ prev,
+                                                      double* __restrict__ sums, int64_t n) {
+  float s_diff = 0.f, s_prev = 0.f;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += (int64_t)gridDim.x * blockDim.x * 2) {
+    const float2 c = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(cur + i));
+    const float2 p = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(prev + i));
+    s_diff += fabsf(bf16_round(c.x - p.x)) + fabsf(bf16_round(c.y - p.y));  // torch.abs(cur - prev) on bf16 tensors
+    s_prev += fabsf(p.x) + fabsf(p.y);
+  }
+  s_diff = warp_sum(s_diff);
+  s_prev = warp_sum(s_prev);
+  __shared__ float sh[2][8];
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { sh[0][w] = s_diff; sh[1][w] = s_prev; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < 8; ++i) { a += sh[0][i]; b += sh[1][i]; }
+    atomicAdd(&sums[0], (double)a);
+    atomicAdd(&sums[1], (double)b);
+  }
+}
+__global__ void ew_addsub_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out,
+                                 int64_t n, int sub) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (i >= n) return;
+  const float2 x = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(a + i));
+  const float2 y = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(b + i));
+  *reinterpret_cast<uint32_t*>(out + i) = sub ? pack_bf16x2(x.x - y.x, x.y - y.y) : pack_bf16x2(x.x + y.x, x.y + y.y);
+}
+}  // namespace ea
+
+extern "C" int ea_l1_sums(const void* cur, const void* prev, void* sums, int64_t n, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  EA_REQUIRE(cur && prev && sums && n > 0 && n % 2 == 0, "ea_l1_sums: bad arguments");
+  cudaMemsetAsync(sums, 0, 2 * sizeof(double), stream);
+  int64_t blocks = (n / 2 + 255) / 256;
+  if (blocks > 4 * ea::sm_count()) blocks = 4 * ea::sm_count();
+  ea::l1_sums_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const ea::bf16*)cur, (const ea::bf16*)prev, (double*)sums, n);
+  ea::count_launch();
+  return ea::check_launch("l1_sums_kernel");
+}
+
+extern "C" int ea_ew_addsub(const void* a, const void* b, void* out, int64_t n, int32_t subtract, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  EA_REQUIRE(a && b && out && n > 0 && n % 2 == 0, "ea_ew_addsub: bad arguments");
+  ea::ew_addsub_kernel<<<(unsigned)((n / 2 + 255) / 256), 256, 0, stream>>>((const ea::bf16*)a, (const ea::bf16*)b,
+                                                                           (ea::bf16*)out, n, subtract);
+  ea::count_launch();
+  return ea::check_launch("ew_addsub_kernel");
+}
