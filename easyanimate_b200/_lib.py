@@ -116,6 +116,8 @@ ea_unpatchify = _sig("ea_unpatchify", [vp, vp, i64, i64, i64, i64, i64, i64, vp]
 ea_attn_fwd = _sig("ea_attn_fwd", [C.POINTER(AttnArgs), vp])
 ea_transpose_v = _sig("ea_transpose_v", [vp, vp, i64, i64, i64, vp])
 ea_cfg_euler_step = _sig("ea_cfg_euler_step", [vp, vp, vp, vp, i64, f32, i32, f32, f32, vp])
+ea_l1_sums = _sig("ea_l1_sums", [vp, vp, vp, i64, vp])
+ea_ew_addsub = _sig("ea_ew_addsub", [vp, vp, vp, i64, i32, vp])
 ea_conv3d_causal = _sig("ea_conv3d_causal", [C.POINTER(ConvArgs), vp])
 ea_vae_prepare_latents = _sig("ea_vae_prepare_latents", [vp, vp, vp, vp, i64, i64, i64, i64, i64, vp])
 ea_groupnorm_workspace = _sig("ea_groupnorm_workspace", [i64, i64], C.c_size_t)

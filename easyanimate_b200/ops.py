@@ -169,6 +169,29 @@ def cfg_euler_step(noise_pred: torch.Tensor, latents: torch.Tensor, guidance_sca
     return out
 
 
+def rel_l1_distance(cur: torch.Tensor, prev: torch.Tensor) -> float:
+    """TeaCache.compute_rel_l1_distance (transformer3d.py:113-117): (|cur-prev|.mean() / |prev|.mean()).item() with the
+    reference's bf16 rounding of each intermediate.  Synchronises the stream (the reference's .cpu().item() does too)."""
+    _req(cur, name="cur"); _req(prev, name="prev")
+    assert cur.shape == prev.shape and cur.is_contiguous() and prev.is_contiguous()
+    sums = torch.empty((2,), device=cur.device, dtype=torch.float64)
+    L.check(L.ea_l1_sums(_p(cur), _p(prev), _p(sums), cur.numel(), _stream()), "ea_l1_sums")
+    num, den = (float(x) for x in sums.cpu())
+    n = cur.numel()
+    mean_diff = torch.tensor(num / n, dtype=torch.float32).to(bf16)  # .mean() of a bf16 tensor is a bf16 scalar
+    mean_prev = torch.tensor(den / n, dtype=torch.float32).to(bf16)
+    return float((mean_diff / mean_prev).item())
+
+
+def ew_add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, subtract: bool = False) -> torch.Tensor:
+    _req(a, name="a"); _req(b, name="b")
+    assert a.shape == b.shape and a.is_contiguous() and b.is_contiguous()
+    if out is None:
+        out = torch.empty_like(a)
+    L.check(L.ea_ew_addsub(_p(a), _p(b), _p(out), a.numel(), int(subtract), _stream()), "ea_ew_addsub")
+    return out
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, S_text: int, *, scale: Optional[float] = None,
               variant: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
     """softmax(q k^T * scale) v for q,k,v [B,H,S,64]; returns (out_text [B,S_text,H*64], out_video [B,S-S_text,H*64])."""

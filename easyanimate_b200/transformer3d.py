@@ -146,6 +146,36 @@ class EasyAnimateDiTBlock(nn.Module):
         return x_v, x_t
 
 
+class TeaCache:
+    """Timestep-embedding-aware step skipping, transformer3d.py:90-121: same counters, thresholds and polynomial
+    rescale as the reference; `previous_modulated_input` / `previous_residual` are device tensors here."""
+
+    def __init__(self, coefficients, num_steps: int, rel_l1_thresh: float = 0.0):
+        if num_steps < 1:
+            raise ValueError(f"`num_steps` must be greater than 0 but is {num_steps}.")
+        if rel_l1_thresh < 0:
+            raise ValueError(f"`rel_l1_thresh` must be greater than or equal to 0 but is {rel_l1_thresh}.")
+        self.coefficients = list(coefficients)
+        self.cnt = 0
+        self.num_steps = num_steps
+        self.rel_l1_thresh = rel_l1_thresh
+        self.accumulated_rel_l1_distance = 0
+        self.previous_modulated_input = None
+        self.previous_residual = None
+        self.skipped = 0
+
+    def rescale_func(self, x: float) -> float:  # np.poly1d(coefficients)(x), highest degree first
+        y = 0.0
+        for c in self.coefficients:
+            y = y * x + c
+        return y
+
+    def reset(self):
+        self.cnt = 0
+        self.previous_modulated_input = None
+        self.previous_residual = None
+
+
 class _Workspace:
     """Per-forward activation buffers shared by all blocks (allocated once per call through torch's caching allocator)."""
 
@@ -239,8 +269,10 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
         self._proj_w_cache: Optional[tuple] = None
 
     # ----------------------------------------------------------------------------------------------------------
-    def enable_teacache(self, num_steps: int, rel_l1_thresh: float, coefficients=None):
-        raise NotImplementedError("TeaCache is a SURVEY.md §8(f) 'next' row and is not implemented in this round")
+    def enable_teacache(self, num_steps: int, rel_l1_thresh: float,
+                        coefficients=(-10.47857366, 8.33844143, -0.78477557, 0.68798618, 0.0136149)):
+        """transformer3d.py:1485-1491. The cache tensors stay on the device (the reference keeps them on the CPU)."""
+        self.teacache = TeaCache(list(coefficients), num_steps, rel_l1_thresh=rel_l1_thresh)
 
     def _set_gradient_checkpointing(self, module, value=False):
         self.gradient_checkpointing = value
@@ -328,16 +360,45 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
 
         # 4. transformer blocks (transformer3d.py:1639-1671)
         ff_inner = self.transformer_blocks[0].ff.net[2].weight.shape[1] if len(self.transformer_blocks) else 4 * d
-        ws = _Workspace(B, S_v, S_t, d, self.num_heads, ff_inner, dev)
-        for block in self.transformer_blocks:
-            x_v, x_t = block(x_v, x_t, temb, rope, ws)
+        # TeaCache decision (transformer3d.py:1563-1586): relative-L1 change of block 0's modulated video input
+        tc = self.teacache
+        should_calc = True
+        if tc is not None:
+            blk0 = self.transformer_blocks[0]
+            mod0 = ops.skinny_linear(temb, blk0.norm1.linear.weight, blk0.norm1.linear.bias, act_in=1)
+            modulated = EasyAnimateDiTBlock._ln_mod(x_v, blk0.norm1, mod0, 0, S_v)
+            if tc.cnt == 0 or tc.cnt == tc.num_steps - 1:
+                tc.accumulated_rel_l1_distance = 0
+            else:
+                dist = ops.rel_l1_distance(modulated, tc.previous_modulated_input)
+                tc.accumulated_rel_l1_distance += tc.rescale_func(dist)
+                if tc.accumulated_rel_l1_distance < tc.rel_l1_thresh:
+                    should_calc = False
+                else:
+                    tc.accumulated_rel_l1_distance = 0
+            tc.previous_modulated_input = modulated
+            tc.cnt += 1
+            if tc.cnt == tc.num_steps:
+                tc.reset()
 
-        # 5. final norms + projection (transformer3d.py:1673-1680): norm_final is row-wise, so the text rows that the
-        #    reference concatenates and then drops never need to be computed.
-        mod = ops.skinny_linear(temb, self.norm_out.linear.weight, self.norm_out.linear.bias, act_in=1)  # [B, 2d] shift|scale
-        y = ops.layernorm_modulate(x_v, self.norm_out.norm.weight, self.norm_out.norm.bias, self.norm_out.norm.eps,
-                                   shift=mod[:, :d], scale=mod[:, d:], rows_per_batch=S_v,
-                                   pre=(self.norm_final.weight, self.norm_final.bias, self.norm_final.eps), out=ws.n_v)
+        if not should_calc:
+            # transformer3d.py:1589-1590: reuse the cached residual; the reference skips the final norms on this path
+            tc.skipped += 1
+            y = ops.ew_add(x_v, tc.previous_residual)
+        else:
+            ori = x_v.clone() if tc is not None else None  # (device copy; the blocks update x_v in place)
+            ws = _Workspace(B, S_v, S_t, d, self.num_heads, ff_inner, dev)
+            for block in self.transformer_blocks:
+                x_v, x_t = block(x_v, x_t, temb, rope, ws)
+
+            # 5. final norms + projection (transformer3d.py:1673-1680): norm_final is row-wise, so the text rows that
+            #    the reference concatenates and then drops never need to be computed.
+            mod = ops.skinny_linear(temb, self.norm_out.linear.weight, self.norm_out.linear.bias, act_in=1)  # shift|scale
+            y = ops.layernorm_modulate(x_v, self.norm_out.norm.weight, self.norm_out.norm.bias, self.norm_out.norm.eps,
+                                       shift=mod[:, :d], scale=mod[:, d:], rows_per_batch=S_v,
+                                       pre=(self.norm_final.weight, self.norm_final.bias, self.norm_final.eps), out=ws.n_v)
+            if tc is not None:
+                tc.previous_residual = ops.ew_add(y, ori, subtract=True)  # transformer3d.py:1634
         z = ops.gemm(y, self.proj_out.weight, self.proj_out.bias)  # [B*S_v, p*p*C_out]
 
         # 6. unpatchify (transformer3d.py:1683-1685); like the reference, the output channel count is taken from the

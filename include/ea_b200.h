@@ -166,6 +166,12 @@ int ea_unpatchify(const void* y, void* out, int64_t B, int64_t C, int64_t F, int
 int ea_cfg_euler_step(const void* pred_uncond, const void* pred_text, const void* x, void* x_out, int64_t n,
                       float guidance_scale, int32_t use_cfg, float sigma, float sigma_next, void* stream);
 
+/* TeaCache support (transformer3d.py:90-121 `compute_rel_l1_distance`, :1563-1636): sums[0] = sum |bf16(cur-prev)|,
+ * sums[1] = sum |prev| (two doubles on the device, zeroed by the call); and out = a +/- b elementwise in bf16
+ * (cached-residual add at :1590, residual capture at :1634). n even. */
+int ea_l1_sums(const void* cur, const void* prev, void* sums, int64_t n, void* stream);
+int ea_ew_addsub(const void* a, const void* b, void* out, int64_t n, int32_t subtract, void* stream);
+
 /* Joint text+video self-attention, non-causal, no mask, head_dim 64:  O = softmax(Q K^T * scale) V.
  * Replaces F.scaled_dot_product_attention + transpose/reshape/split at processor.py:287-303.
  * q,k,v: [B,H,S,64] bf16 contiguous.  Output is token-major and split at S_text:

@@ -285,6 +285,16 @@ class EasyAnimateDiTBlock(nn.Module):
         return hidden_states, encoder_hidden_states
 
 
+class OracleTeaCache:
+    """transformer3d.py:90-121 state holder (the decision logic is restated inside OracleTransformer3D.forward)."""
+
+    def __init__(self, coefficients, num_steps, rel_l1_thresh=0.0):
+        self.coefficients, self.num_steps, self.rel_l1_thresh = list(coefficients), num_steps, rel_l1_thresh
+        self.cnt, self.accumulated_rel_l1_distance, self.skipped = 0, 0, 0
+        self.previous_modulated_input = None
+        self.previous_residual = None
+
+
 class OracleTransformer3D(nn.Module):
     """transformer3d.py:1346-1689, v5.1 configuration space (no ref/clip/control branches, no TeaCache)."""
 
@@ -336,12 +346,39 @@ class OracleTransformer3D(nn.Module):
         if encoder_hidden_states_t5 is not None:
             encoder_hidden_states_t5 = self.text_proj_t5(encoder_hidden_states_t5)
             encoder_hidden_states = torch.cat([encoder_hidden_states, encoder_hidden_states_t5], dim=1).contiguous()
-        for block in self.transformer_blocks:
-            hidden_states, encoder_hidden_states = block(hidden_states, encoder_hidden_states, temb, image_rotary_emb)
-        hidden_states = torch.cat([encoder_hidden_states, hidden_states], dim=1)
-        hidden_states = self.norm_final(hidden_states)
-        hidden_states = hidden_states[:, encoder_hidden_states.size()[1]:]
-        hidden_states = self.norm_out(hidden_states, temb=temb)
+        # TeaCache (transformer3d.py:1563-1636)
+        tc = getattr(self, "teacache", None)
+        should_calc = True
+        if tc is not None:
+            modulated_inp, _, _, _ = self.transformer_blocks[0].norm1(hidden_states.clone(), encoder_hidden_states.clone(),
+                                                                      temb.clone())
+            if tc.cnt == 0 or tc.cnt == tc.num_steps - 1:
+                tc.accumulated_rel_l1_distance = 0
+            else:
+                prev = tc.previous_modulated_input
+                rel = ((torch.abs(modulated_inp - prev).mean()) / torch.abs(prev).mean()).item()
+                tc.accumulated_rel_l1_distance += float(np.poly1d(tc.coefficients)(rel))
+                if tc.accumulated_rel_l1_distance < tc.rel_l1_thresh:
+                    should_calc = False
+                else:
+                    tc.accumulated_rel_l1_distance = 0
+            tc.previous_modulated_input = modulated_inp
+            tc.cnt += 1
+            if tc.cnt == tc.num_steps:
+                tc.cnt, tc.previous_modulated_input, tc.previous_residual = 0, None, None
+        if not should_calc:
+            tc.skipped += 1
+            hidden_states = hidden_states + tc.previous_residual
+        else:
+            ori_hidden_states = hidden_states.clone()
+            for block in self.transformer_blocks:
+                hidden_states, encoder_hidden_states = block(hidden_states, encoder_hidden_states, temb, image_rotary_emb)
+            hidden_states = torch.cat([encoder_hidden_states, hidden_states], dim=1)
+            hidden_states = self.norm_final(hidden_states)
+            hidden_states = hidden_states[:, encoder_hidden_states.size()[1]:]
+            hidden_states = self.norm_out(hidden_states, temb=temb)
+            if tc is not None:
+                tc.previous_residual = hidden_states - ori_hidden_states
         hidden_states = self.proj_out(hidden_states)
         output = hidden_states.reshape(batch_size, video_length, height // p, width // p, channels, p, p)
         output = output.permute(0, 4, 1, 2, 5, 3, 6).flatten(5, 6).flatten(3, 4)

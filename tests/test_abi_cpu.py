@@ -54,6 +54,8 @@ def test_transformer_config_surface_and_keys():
     assert m.config.get("time_position_encoding_type", "2d_rope") == "3d_rope"
     assert m.config.get("not_there", 7) == 7 and m.config.enable_text_attention_mask is True
     assert m.resize_inpaint_mask_directly is False and m.enable_clip_in_inpaint is True and m.teacache is None
+    m.enable_teacache(25, 0.08)
+    assert m.teacache.num_steps == 25 and abs(m.teacache.rescale_func(0.1) - float(__import__('numpy').poly1d(m.teacache.coefficients)(0.1))) < 1e-9
     assert set(m.state_dict().keys()) == set(dit.OracleTransformer3D(**cfg).state_dict().keys())
     assert m.to(torch.bfloat16).dtype == torch.bfloat16
     with pytest.raises(ValueError):

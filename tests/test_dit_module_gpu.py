@@ -85,3 +85,29 @@ def test_config_surface_and_state_dict_keys():
     assert m.config.get("time_position_encoding_type", "2d_rope") == "3d_rope"
     assert m.config.get("not_there", 7) == 7 and m.config.enable_text_attention_mask is True
     assert set(m.state_dict().keys()) == set(dit.OracleTransformer3D(**CFG_TINY).state_dict().keys())
+
+
+def test_teacache_matches_oracle_decisions_and_outputs():
+    """TeaCache (transformer3d.py:90-121,1563-1636): same skip decisions and outputs as the oracle over a 6-step loop."""
+    from oracle import dit
+    o32, ob, ours = _build(CFG_TINY)
+    coeffs = [1.07862322, -4.19362456, 3.06725828, 0.33161686, 0.02374758]  # get_teacache_coefficients("v5.1-7b")
+    steps, thresh = 6, 0.08
+    ob.teacache = dit.OracleTeaCache(coeffs, steps, thresh)
+    ours.enable_teacache(steps, thresh, coefficients=coeffs)
+    B, C, F, H, W, S_t = 2, 16, 2, 8, 8, 16
+    lat, enc, _ = _inputs(B, C, F, H, W, S_t, CFG_TINY["text_embed_dim"])
+    rope = dit.rope_for_video(H * 8, W * 8, F)
+    sched = dit.FlowMatchEulerScheduler()
+    sched.set_timesteps(steps)
+    x_ref, x_our = lat.to(bf16), lat.to(bf16).cuda()
+    with torch.no_grad():
+        for t in sched.timesteps:
+            tb = torch.tensor([t, t]).to(bf16)
+            r = ob(x_ref, tb, encoder_hidden_states=enc.to(bf16), image_rotary_emb=rope)[0]
+            g = ours(x_our, tb.cuda(), encoder_hidden_states=enc.to(bf16).cuda(),
+                     image_rotary_emb=(rope[0].cuda(), rope[1].cuda()), return_dict=False)[0]
+            torch.testing.assert_close(g.float().cpu(), r.float(), rtol=0.05, atol=0.05)
+            x_ref, x_our = (x_ref - 0.1 * r).to(bf16), (x_our - 0.1 * g).to(bf16)
+    assert ours.teacache.skipped == ob.teacache.skipped and ours.teacache.skipped >= 1, (ours.teacache.skipped, ob.teacache.skipped)
+    assert ours.teacache.cnt == 0  # reset after num_steps forwards, like the reference
