@@ -6,14 +6,14 @@
 // `tcgen05.ld.32x32b.x32` in that window - i.e. ~64 B/clk/SM of TMEM read bandwidth, the same figure the B300
 // micro-architecture notes give for LDTM.  At head_dim 64 a 128x128 fp32 score tile therefore costs ~1024 cycles to
 // read and ~1024 cycles of MUFU.EX2 (16/clk/SM), against 512 tensor cycles: the kernel is bound by those two units.
-// So: each softmax thread reads its 128 scores ONCE into registers (10 warps => up to 204 registers per thread),
+// So: each softmax thread reads its 128 scores ONCE into registers (setmaxnreg: 216 registers for the softmax warps),
 // releases the S buffer immediately (the MMA warp issues QK_{j+1} while this block is still being exponentiated), and
 // the two tiles ping-pong so one tile's TMEM-read phase overlaps the other tile's exp phase.
 //
 //   TMEM (512 columns): S_t at 128 t | P_t (packed bf16) at 256 + 64 t | O_t at 384 + 64 t
 //   warps 0-3 / 4-7 : softmax of tile A / B, one query row per thread
 //   warp 8          : TMA producer (Q once, K_j / V_j 128-key tiles through 4-stage rings)
-//   warp 9          : TMEM allocator, then MMA issuer
+//   warp 9          : TMEM allocator, then MMA issuer;  warps 10-11: idle (complete the third warpgroup)
 #include "common.cuh"
 #include "host.h"
 #include "../../include/ea_b200.h"
@@ -24,7 +24,7 @@ extern void count_launch();
 
 namespace a4 {
 
-constexpr int kThreads = 320;
+constexpr int kThreads = 384;
 constexpr int kQT = 128;
 constexpr int kKT = 128;
 constexpr int kHD = 64;
@@ -85,10 +85,11 @@ EA_DEVICE float exp2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(y) << 23));
 }
 
-// 320 threads x 200 registers = 64 000 of the SM's 65 536: __launch_bounds__(320, 1) would make ptxas budget for a
-// 384-thread block (168 registers) and spill the score row.
+// Register budget: each SM sub-partition owns 16 384 registers and hosts 3 of the 12 warps: the two softmax warps
+// grow to 216 registers with setmaxnreg (they hold a 128-column score row), the producer/MMA warpgroup shrinks to 72
+// (2 x 216 + 72 = 3 x 168, the launch-time allocation).
 template <int POLY>
-__global__ void __maxnreg__(200)
+__global__ void __launch_bounds__(kThreads, 1)
 attn4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
              const __grid_constant__ CUtensorMap tmap_v, const Args p) {
   extern __shared__ uint8_t smem_raw[];
@@ -142,6 +143,9 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp >= 8) {
+  // ---- producer / MMA warpgroup: give registers back
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
   if (warp == 8) {
     if (lane == 0) {
       // ===== TMA producer =====
@@ -216,7 +220,10 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         umma_commit(&v_empty[st]);
       }
     }
+  }
   } else {
+    // ---- softmax warpgroups: take them
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     // ===== softmax / correction / epilogue: tile t, one query row per thread =====
     const int t = warp >> 2;
     const int ew = warp & 3;
