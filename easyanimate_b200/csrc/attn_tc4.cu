@@ -125,9 +125,9 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     mbar_init(q_full, 1);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
+      mbar_init(&k_empty[i], 2);  // one tcgen05.commit per tile issuer
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&v_empty[i], 2);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
@@ -163,9 +163,12 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         if (++st == kStages) { st = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp <= 10) {
     if (lane == 0) {
-      // ===== MMA issuer =====
+      // ===== MMA issuers: warp 9 drives tile A, warp 10 drives tile B, independently =====
+      // (one issuer walking both tiles in a fixed order head-of-line blocks: it sits in wait(p_ready[A]) while
+      //  s_free[B] has long fired, the tiles lock IN phase and the TMEM-read and exp phases never overlap.)
+      const int t = warp - 9;
       constexpr uint32_t idesc_qk = umma_idesc_bf16(kQT, kKT, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(kQT, kHD, 0, 1);  // V: MN-major B operand
       mbar_wait(q_full, 0);
@@ -191,32 +194,22 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
       };
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      issue_qk(0, 0);
-      issue_qk(1, 0);
-      umma_commit(&k_empty[0]);
+      issue_qk(t, 0);
+      umma_commit(&k_empty[0]);  // K/V stages are released when BOTH issuers have committed (barrier count 2)
       for (int j = 0; j < nblk; ++j) {
         const int st = j % kStages;
         const uint32_t par = j & 1;
-        const bool more = j + 1 < nblk;
-        if (more) {
-          mbar_wait(&s_free[0], par);  // tile A's softmax has pulled S_A(j) into registers
+        if (j + 1 < nblk) {
+          mbar_wait(&s_free[t], par);  // this tile's softmax has pulled S(j) into registers
           mbar_wait(&k_full[(j + 1) % kStages], ((j + 1) / kStages) & 1);
           tc_fence_after();
-          issue_qk(0, j + 1);
-        }
-        mbar_wait(&p_ready[0], par);
-        mbar_wait(&v_full[st], (j / kStages) & 1);
-        tc_fence_after();
-        issue_pv(0, j);
-        if (more) {
-          mbar_wait(&s_free[1], par);
-          tc_fence_after();
-          issue_qk(1, j + 1);
+          issue_qk(t, j + 1);
           umma_commit(&k_empty[(j + 1) % kStages]);
         }
-        mbar_wait(&p_ready[1], par);
+        mbar_wait(&p_ready[t], par);
+        mbar_wait(&v_full[st], (j / kStages) & 1);
         tc_fence_after();
-        issue_pv(1, j);
+        issue_pv(t, j);
         umma_commit(&v_empty[st]);
       }
     }
@@ -236,6 +229,9 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     float l = 0.f;
     for (int j = 0; j < nblk; ++j) {
       mbar_wait(&s_full[t], j & 1);
+      // start the two tiles half a period apart: tile B reads its first scores when tile A starts exponentiating,
+      // so that from then on one tile's TMEM-read phase runs under the other tile's MUFU phase
+      if (t == 1 && j == 0) mbar_wait(&s_free[0], 0);
       tc_fence_after();
       uint32_t s[kKT];
       tmem_ld32p(tS, s);
