@@ -5,6 +5,7 @@ the stream owner here; none of these functions computes anything with torch ops.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -13,6 +14,9 @@ from . import _lib as L
 
 bf16 = torch.bfloat16
 ATTN_TIMING = None  # set to a list by bench.py to collect (start, end) CUDA events around every attention launch
+# attention kernel selector (include/ea_b200.h `ea_attn_args.variant`): 0x2c = one-pass two-tile kernel with 2 of every
+# 8 exponentials on the FMA pipe — the fastest measured on B200 (profiles/r01_attn_microbench_*.log)
+ATTN_VARIANT = int(os.environ.get("EA_ATTN_VARIANT", "0x2c"), 0)
 
 
 def _stream() -> int:
@@ -193,7 +197,7 @@ def ew_add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None,
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, S_text: int, *, scale: Optional[float] = None,
-              variant: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
+              variant: int = ATTN_VARIANT) -> Tuple[torch.Tensor, torch.Tensor]:
     """softmax(q k^T * scale) v for q,k,v [B,H,S,64]; returns (out_text [B,S_text,H*64], out_video [B,S-S_text,H*64])."""
     _req(q, name="q"); _req(k, name="k"); _req(v, name="v")
     B, H, S, hd = q.shape

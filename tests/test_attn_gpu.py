@@ -1,0 +1,47 @@
+"""tcgen05 attention kernels against an fp32 PyTorch reference of softmax(QK^T/sqrt(64))V (GPU only)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+bf16 = torch.bfloat16
+
+# 0x2c: default (one-pass two-tile kernel, 2 of 8 exponentials by polynomial); 0x0c: same, all MUFU; 1: first generation
+VARIANTS = [0x2C, 0x0C, 0x1, 0x24, 0x28]
+SHAPES = [(1, 2, 128, 0), (1, 2, 256, 64), (2, 3, 1000, 77), (1, 4, 4176, 256), (1, 1, 8, 3), (2, 2, 300, 300)]
+
+
+def _ref(q, k, v):
+    B, H, S, _ = q.shape
+    return torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float()).transpose(1, 2).reshape(B, S, H * 64)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("B,H,S,St", SHAPES)
+def test_attention_matches_fp32_reference(variant, B, H, S, St):
+    from easyanimate_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(S + variant)
+    q, k, v = [torch.randn(B, H, S, 64, device="cuda", generator=g).to(bf16) for _ in range(3)]
+    ot, ov = ops.attention(q, k, v, St, variant=variant)
+    assert ot.shape == (B, St, H * 64) and ov.shape == (B, S - St, H * 64)
+    got = torch.cat([ot, ov], 1).float()
+    ref = _ref(q, k, v)
+    # bf16 P and bf16 output: a few 1e-3 absolute on outputs of O(0.1-1)
+    torch.testing.assert_close(got, ref, rtol=2e-2, atol=4e-3)
+
+
+def test_attention_large_logits_and_running_max_rescale():
+    """Scores that keep growing along the key axis force the lazy running-max rescale path of every kernel."""
+    from easyanimate_b200 import ops
+    B, H, S = 1, 2, 1024
+    g = torch.Generator(device="cuda").manual_seed(7)
+    q = torch.randn(B, H, S, 64, device="cuda", generator=g)
+    k = torch.randn(B, H, S, 64, device="cuda", generator=g)
+    ramp = torch.linspace(0, 6, S, device="cuda").view(1, 1, S, 1)
+    k = k + ramp * q.mean(dim=2, keepdim=True).sign()  # later keys align more and more with the queries
+    q, k = (q * 3).to(bf16), k.to(bf16)
+    v = torch.randn(B, H, S, 64, device="cuda", generator=g).to(bf16)
+    ref = _ref(q, k, v)
+    for variant in VARIANTS:
+        ot, ov = ops.attention(q, k, v, 0, variant=variant)
+        assert torch.isfinite(ov).all()
+        torch.testing.assert_close(ov.float(), ref, rtol=3e-2, atol=2e-2)
