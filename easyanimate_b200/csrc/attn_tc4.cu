@@ -233,23 +233,27 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
       // so that from then on one tile's TMEM-read phase runs under the other tile's MUFU phase
       if (t == 1 && j == 0) mbar_wait(&s_free[0], 0);
       tc_fence_after();
+      // One tcgen05.ld in flight at a time: measured (profiles/r01_tmem_microbench.log) a warp sustains ~72 B/clk with
+      // wait-after-each but only ~33 B/clk with four loads outstanding. The row max of chunk c runs under load c+1.
       uint32_t s[kKT];
+      const int valid = p.S - j * kKT;  // < 128 only in the last block (TMA zero-filled the missing keys)
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       tmem_ld32p(tS, s);
-      tmem_ld32p(tS + 32, s + 32);
-      tmem_ld32p(tS + 64, s + 64);
-      tmem_ld32p(tS + 96, s + 96);
       tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < 3) tmem_ld32p(tS + (c + 1) * 32, s + (c + 1) * 32);
+        if (valid < kKT) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid) s[c * 32 + i] = 0xff800000u;  // -inf
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(s[c * 32 + i]));
+        if (c < 3) tmem_ld_wait();
+      }
       tc_fence_before();
       mbar_arrive(&s_free[t]);  // S_t may be overwritten by QK_{j+1}
-      const int valid = p.S - j * kKT;
-      if (valid < kKT) {  // last block: keys beyond S were zero-filled by TMA
-#pragma unroll
-        for (int i = 0; i < kKT; ++i)
-          if (i >= valid) s[i] = 0xff800000u;  // -inf
-      }
-      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-      for (int i = 0; i < kKT; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(s[i]));
       const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
       if (j > 0) {
         // PV_{j-1} must have finished reading P_t before it is overwritten, and O_t must be complete for a rescale

@@ -32,8 +32,8 @@ EA_DEVICE float2 unpack_bf16x2(uint32_t u) {
 
 // A kernel that waits on an mbarrier which never completes would hang the GPU box; every wait is
 // bounded and traps (kills the context, surfaces as a CUDA error on the host) instead.
-#ifndef EA_MBAR_SPIN_LIMIT
-#define EA_MBAR_SPIN_LIMIT (1u << 24)
+#ifndef EA_MBAR_TIMEOUT_NS
+#define EA_MBAR_TIMEOUT_NS 20000000000ull  // 20 s
 #endif
 
 // ----------------------------------------------------------------------------------------------
@@ -54,19 +54,30 @@ EA_DEVICE void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 EA_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+  // the suspend-time hint lets the hardware park the thread until the phase completes instead of returning after the
+  // short default window: without it ncu showed the producer/MMA threads re-polling millions of times and taking
+  // issue slots from the softmax warps of the same SM sub-partition
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok != 0;
 }
+EA_DEVICE uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 EA_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > EA_MBAR_SPIN_LIMIT) {
+    // wall-clock bound (each try_wait may park the thread for up to the suspend hint): trap instead of hanging the box
+    if ((++spins & 63u) == 0 && global_timer_ns() - t0 > EA_MBAR_TIMEOUT_NS) {
       printf("ea_b200: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
       __trap();
     }
