@@ -88,6 +88,22 @@ EA_DEVICE float exp2_poly(float x) {
 // Register budget: each SM sub-partition owns 16 384 registers and hosts 3 of the 12 warps: the two softmax warps
 // grow to 216 registers with setmaxnreg (they hold a 128-column score row), the producer/MMA warpgroup shrinks to 72
 // (2 x 216 + 72 = 3 x 168, the launch-time allocation).
+// the same on a pair of columns with packed fp32x2 instructions (3 FADD2/FFMA2 for the split, 3 FFMA2 for the polynomial)
+EA_DEVICE float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 y = __fadd2_rn(x, make_float2(12582912.0f, 12582912.0f));
+  const float2 n = __fadd2_rn(y, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = __ffma2_rn(n, make_float2(-1.0f, -1.0f), x);
+  float2 q = __ffma2_rn(f, make_float2(0.05500892f, 0.05500892f), make_float2(0.24221097f, 0.24221097f));
+  q = __ffma2_rn(q, f, make_float2(0.69328290f, 0.69328290f));
+  q = __ffma2_rn(q, f, make_float2(1.0f, 1.0f));
+  float2 e;
+  e.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(y.x) << 23));
+  e.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(y.y) << 23));
+  return e;
+}
+
 template <int POLY>
 __global__ void __launch_bounds__(kThreads, 1)
 attn4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -281,23 +297,30 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
           m_ref = m_new;
         }
       }
-      const float neg_m = -m_ref;
-      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+      // Packed fp32x2 arithmetic (Blackwell FFMA2/FADD2: two lanes per issue slot) for the scale-subtract, the row sum
+      // and the polynomial; POLY of every 4 column PAIRS take the FMA-pipe exp2, the rest MUFU.EX2.
+      const float2 c2 = make_float2(p.scale_log2, p.scale_log2);
+      const float2 nm2 = make_float2(-m_ref, -m_ref);
+      float2 acc2[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float x0 = fmaf(__uint_as_float(s[c * 32 + i]), p.scale_log2, neg_m);
-          const float x1 = fmaf(__uint_as_float(s[c * 32 + i + 1]), p.scale_log2, neg_m);
-          const float e0 = ((i & 7) < POLY) ? exp2_poly(x0) : ex2(x0);
-          const float e1 = (((i + 1) & 7) < POLY) ? exp2_poly(x1) : ex2(x1);
-          s4[(i >> 1) & 3] += e0 + e1;
-          pk[i >> 1] = pack_bf16x2(e0, e1);
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c * 32 + i]), __uint_as_float(s[c * 32 + i + 1])), c2, nm2);
+          float2 e;
+          if (((i >> 1) & 3) < POLY) {
+            e = exp2_poly2(x);
+          } else {
+            e.x = ex2(x.x);
+            e.y = ex2(x.y);
+          }
+          acc2[(i >> 1) & 3] = __fadd2_rn(acc2[(i >> 1) & 3], e);
+          pk[i >> 1] = pack_bf16x2(e.x, e.y);
         }
         tmem_st16(tP + c * 16, pk);
       }
-      l += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      l += ((acc2[0].x + acc2[0].y) + (acc2[1].x + acc2[1].y)) + ((acc2[2].x + acc2[2].y) + (acc2[3].x + acc2[3].y));
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_ready[t]);
