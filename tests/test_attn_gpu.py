@@ -5,8 +5,9 @@ import torch
 pytestmark = pytest.mark.gpu
 bf16 = torch.bfloat16
 
-# 0x2c: default (one-pass two-tile kernel, 2 of 8 exponentials by polynomial); 0x0c: same, all MUFU; 1: first generation
-VARIANTS = [0x2C, 0x0C, 0x1, 0x24, 0x28]
+# 0x1c: default (one-pass two-tile kernel, 1 of 4 column pairs by polynomial); 0x0c: all MUFU; 0x3c: 3 of 4 pairs by
+# polynomial; 1: first generation; 0x24 / 0x28: second / third generation
+VARIANTS = [0x1C, 0x0C, 0x3C, 0x1, 0x24, 0x28]
 SHAPES = [(1, 2, 128, 0), (1, 2, 256, 64), (2, 3, 1000, 77), (1, 4, 4176, 256), (1, 1, 8, 3), (2, 2, 300, 300)]
 
 
