@@ -150,8 +150,8 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], 4);   // one arrive per softmax warp (128 per-thread arrives serialise on the barrier word)
-      mbar_init(&p_ready[i], 4);
+      mbar_init(&s_free[i], 128);
+      mbar_init(&p_ready[i], 128);
       mbar_init(&o_done[i], 1);
     }
     fence_mbar_init();
@@ -272,8 +272,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         if (c < 3) tmem_ld_wait();
       }
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[t]);  // S_t may be overwritten by QK_{j+1}
+      mbar_arrive(&s_free[t]);  // S_t may be overwritten by QK_{j+1}
       const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
       if (j > 0) {
         // PV_{j-1} must have finished reading P_t before it is overwritten, and O_t must be complete for a rescale
@@ -327,8 +326,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
       l += ((acc2[0].x + acc2[0].y) + (acc2[1].x + acc2[1].y)) + ((acc2[2].x + acc2[2].y) + (acc2[3].x + acc2[3].y));
       tmem_st_wait();
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_ready[t]);
+      mbar_arrive(&p_ready[t]);
     }
     mbar_wait(&o_done[t], (nblk - 1) & 1);
     tc_fence_after();
