@@ -252,6 +252,12 @@ class AutoencoderKLMagvit(nn.Module, ConfigMixinLite):
         self.tile_overlap_factor = tile_overlap_factor
         self.tile_latent_min_size = int(self.tile_sample_min_size / (2 ** (len(ch_mult) - 1)))
         self.scaling_factor = scaling_factor
+        self.tile_parallel_group = None  # torch.distributed group for tile-parallel tiled_decode (one all-gather)
+
+    def set_tile_parallel_group(self, group):
+        """Shard the reference's tiled_decode tiles over the ranks of `group` (every rank must call decode with the
+        same latents); None restores single-GPU decoding."""
+        self.tile_parallel_group = group
 
     # ----------------------------------------------------------------------------------------------------------
     def _decode_one(self, z: torch.Tensor) -> torch.Tensor:
@@ -266,12 +272,13 @@ class AutoencoderKLMagvit(nn.Module, ConfigMixinLite):
         overlap_size = int(tl * (1 - self.tile_overlap_factor))
         blend_extent = int(self.tile_sample_min_size * self.tile_overlap_factor)
         row_limit = self.tile_sample_min_size - blend_extent
-        rows = []
-        for i in range(0, z.shape[2], overlap_size):
-            row = []
-            for j in range(0, z.shape[3], overlap_size):
-                row.append(self._decode_one(z[:, :, i:i + tl, j:j + tl].contiguous()))
-            rows.append(row)
+        coords = [[(i, j) for j in range(0, z.shape[3], overlap_size)] for i in range(0, z.shape[2], overlap_size)]
+        group = self.tile_parallel_group
+        if group is None:
+            rows = [[self._decode_one(z[:, :, i:i + tl, j:j + tl].contiguous()) for (i, j) in row] for row in coords]
+            lower_right = None
+        else:
+            rows, lower_right = self._decode_tiles_parallel(z, coords, tl, group)
         Tp = rows[0][0].shape[2]
         widths = [min(t.shape[4], row_limit) for t in rows[0]]
         heights = [min(r[0].shape[3], row_limit) for r in rows]
@@ -287,9 +294,39 @@ class AutoencoderKLMagvit(nn.Module, ConfigMixinLite):
                 vae_ops.copy2d(tile, dec, heights[i], widths[j], r0, c0)
                 c0 += widths[j]
             r0 += heights[i]
-        lower_right = self._decode_one(z[:, :, -tl:, -tl:].contiguous())
+        if lower_right is None:
+            lower_right = self._decode_one(z[:, :, -tl:, -tl:].contiguous())
         vae_ops.corner_blend(lower_right, dec)
         return dec
+
+    def _decode_tiles_parallel(self, z, coords, tl, group):
+        """Tile-parallel decode: the reference's tiles are independent decoder passes
+        (autoencoder_magvit.py:389-402,418-426), so rank r decodes tiles r, r+N, ... of the row-major tile list
+        (+ the lower-right corner pass as the last entry) and ONE all-gather of the padded tiles makes every rank
+        hold all of them; blending then runs identically on every rank."""
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        flat = [c for row in coords for c in row]
+        specs = [z[:, :, i:i + tl, j:j + tl] for (i, j) in flat] + [z[:, :, -tl:, -tl:]]
+        per_rank = (len(specs) + world - 1) // world
+        Tp = 4 * (z.shape[1] - 1) + 1
+        buf = torch.zeros((per_rank, self.config.out_channels, Tp, 8 * tl, 8 * tl), device=z.device, dtype=bf16)
+        for slot, k in enumerate(k for k in range(len(specs)) if k % world == rank):
+            out = self._decode_one(specs[k].contiguous())  # [1,3,T',8h,8w]
+            vae_ops.copy2d(out, buf[slot:slot + 1], out.shape[3], out.shape[4], 0, 0)
+        gathered = torch.empty((world * per_rank,) + tuple(buf.shape[1:]), device=z.device, dtype=bf16)
+        dist.all_gather_into_tensor(gathered, buf, group=group)  # rank r's slots land at [r*per_rank, (r+1)*per_rank)
+
+        def tile(k):
+            hk, wk = 8 * specs[k].shape[2], 8 * specs[k].shape[3]
+            return gathered[(k % world) * per_rank + k // world][None, :, :, :hk, :wk]
+
+        rows, k = [], 0
+        for row in coords:
+            rows.append([tile(k + n) for n in range(len(row))])
+            k += len(row)
+        return rows, tile(len(specs) - 1).contiguous()
 
     def _decode(self, z: torch.Tensor) -> torch.Tensor:
         if self.upcast_vae:

@@ -123,24 +123,30 @@ def tile_blend(a: torch.Tensor, b: torch.Tensor, extent: int, axis: int) -> None
     else:
         extent = min(Wa, Wb, extent)
         rows, cols, off_r, off_c = min(Ha, Hb), extent, 0, Wa - extent
-    assert a.is_contiguous() and b.is_contiguous()
-    L.check(L.ea_tile_blend(_p(a), Ha * Wa, Wa, off_r, off_c, _p(b), Hb * Wb, Wb, planes, rows, cols, extent, axis,
+    (pa, la), (pb, lb) = _planar(a), _planar(b)
+    L.check(L.ea_tile_blend(_p(a), pa, la, off_r, off_c, _p(b), pb, lb, planes, rows, cols, extent, axis,
                             _stream()), "ea_tile_blend")
+
+
+def _planar(t: torch.Tensor):
+    """(plane stride, row stride) of a [1,C,T,H,W] tensor or crop view whose C*T planes are uniformly strided."""
+    assert t.dim() == 5 and t.shape[0] == 1 and t.stride(4) == 1 and t.stride(1) == t.shape[2] * t.stride(2), t.stride()
+    return t.stride(2), t.stride(3)
 
 
 def copy2d(src: torch.Tensor, dst: torch.Tensor, rows: int, cols: int, dst_r0: int, dst_c0: int) -> None:
     """dst[..., dst_r0:dst_r0+rows, dst_c0:dst_c0+cols] = src[..., :rows, :cols] for contiguous [..,H,W] tensors."""
     planes = src.shape[0] * src.shape[1] * src.shape[2]
-    Hs, Ws, Hd, Wd = src.shape[3], src.shape[4], dst.shape[3], dst.shape[4]
-    assert src.is_contiguous() and dst.is_contiguous()
-    dptr = dst.data_ptr() + (dst_r0 * Wd + dst_c0) * 2
-    L.check(L.ea_copy2d(_p(src), Hs * Ws, Ws, dptr, Hd * Wd, Wd, planes, rows, cols, _stream()), "ea_copy2d")
+    (ps, ls), (pd, ld) = _planar(src), _planar(dst)
+    dptr = dst.data_ptr() + (dst_r0 * ld + dst_c0) * 2
+    L.check(L.ea_copy2d(_p(src), ps, ls, dptr, pd, ld, planes, rows, cols, _stream()), "ea_copy2d")
 
 
 def corner_blend(src: torch.Tensor, dst: torch.Tensor) -> None:
     """dst[..., -H:, -W:] = w*src + (1-w)*dst[..., -H:, -W:] (autoencoder_magvit.py:429-443)."""
     planes = src.shape[0] * src.shape[1] * src.shape[2]
     Hc, Wc, Hd, Wd = src.shape[3], src.shape[4], dst.shape[3], dst.shape[4]
-    assert src.is_contiguous() and dst.is_contiguous()
-    dptr = dst.data_ptr() + ((Hd - Hc) * Wd + (Wd - Wc)) * 2
-    L.check(L.ea_corner_blend(_p(src), dptr, Hd * Wd, Wd, planes, Hc, Wc, _stream()), "ea_corner_blend")
+    assert src.is_contiguous()
+    pd, ld = _planar(dst)
+    dptr = dst.data_ptr() + ((Hd - Hc) * ld + (Wd - Wc)) * 2
+    L.check(L.ea_corner_blend(_p(src), dptr, pd, ld, planes, Hc, Wc, _stream()), "ea_corner_blend")
