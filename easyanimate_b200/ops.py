@@ -14,9 +14,10 @@ from . import _lib as L
 
 bf16 = torch.bfloat16
 ATTN_TIMING = None  # set to a list by bench.py to collect (start, end) CUDA events around every attention launch
-# attention kernel selector (include/ea_b200.h `ea_attn_args.variant`): 0x1c = one-pass two-tile kernel with 1 of every
-# 4 column pairs exponentiated on the FMA pipe — the fastest measured on B200 (profiles/r01_attn_microbench_*.log)
-ATTN_VARIANT = int(os.environ.get("EA_ATTN_VARIANT", "0x1c"), 0)
+# attention kernel selector (include/ea_b200.h `ea_attn_args.variant`): 0x10c = sixth-generation kernel (one TMEM pass,
+# no per-block row maximum on the hot path, all exponentials on MUFU) — the fastest measured on B200
+# (profiles/r01_attn_microbench_*.log); 0x1c = fourth generation with 1 of 4 column pairs on the FMA pipe
+ATTN_VARIANT = int(os.environ.get("EA_ATTN_VARIANT", "0x10c"), 0)
 
 
 def _stream() -> int:

@@ -176,10 +176,14 @@ int ea_ew_addsub(const void* a, const void* b, void* out, int64_t n, int32_t sub
  * Replaces F.scaled_dot_product_attention + transpose/reshape/split at processor.py:287-303.
  * q,k,v: [B,H,S,64] bf16 contiguous.  Output is token-major and split at S_text:
  * out_text[B,S_text,H*64], out_video[B,S-S_text,H*64].
- * variant: bit2 set (the default used by the Python layer: 0x34) = two-query-tile ping-pong kernel, bits 4-6 = how
- * many of every 8 exponentials are evaluated by a polynomial on the FMA pipe instead of MUFU (0,2,3,4,5).
- * bit2 clear = first-generation one-tile kernel: bit0 P operand through TMEM instead of shared memory; bit1 v is
- * pre-transposed [B,H,64,S_pad] (see ea_transpose_v). */
+ * variant selects the kernel generation (all produce the same softmax; kept for A/B measurements, profiles/):
+ *   bit8 (0x100, the Python layer's default is 0x10c): sixth generation - two query tiles per CTA, one TMEM pass,
+ *     exponentials against the reference kept from earlier key blocks with an end-of-block overflow check instead of
+ *     a per-block row maximum;  bit7 (0x80): fifth generation - score columns split over two warps (16 softmax warps);
+ *   bits 2+3 (0x0c): fourth generation (per-block row maximum, lazy rescale);  bit3 / bit2 alone: third / second;
+ *   bits 4-6: how many of every 4 column pairs are exponentiated by a polynomial on the FMA pipe instead of MUFU;
+ *   none of bits 2,3,7,8: first-generation one-tile kernel - bit0: P operand through TMEM instead of shared memory,
+ *   bit1: v is pre-transposed [B,H,64,S_pad] (see ea_transpose_v). */
 typedef struct {
   const void* q;
   const void* k;

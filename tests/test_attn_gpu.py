@@ -7,7 +7,8 @@ bf16 = torch.bfloat16
 
 # 0x1c: default (one-pass two-tile kernel, 1 of 4 column pairs by polynomial); 0x0c: all MUFU; 0x3c: 3 of 4 pairs by
 # polynomial; 1: first generation; 0x24 / 0x28: second / third generation
-VARIANTS = [0x1C, 0x0C, 0x3C, 0x1, 0x24, 0x28]
+# 0x9c / 0x8c: column-split softmax (16 softmax warps); 0x11c / 0x10c / 0x12c: optimistic reference (no hot-path row max)
+VARIANTS = [0x1C, 0x0C, 0x3C, 0x11C, 0x10C, 0x12C, 0x9C, 0x8C, 0x1, 0x24, 0x28]
 SHAPES = [(1, 2, 128, 0), (1, 2, 256, 64), (2, 3, 1000, 77), (1, 4, 4176, 256), (1, 1, 8, 3), (2, 2, 300, 300)]
 
 
@@ -46,3 +47,24 @@ def test_attention_large_logits_and_running_max_rescale():
         ot, ov = ops.attention(q, k, v, 0, variant=variant)
         assert torch.isfinite(ov).all()
         torch.testing.assert_close(ov.float(), ref, rtol=3e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("variant", [0x11C, 0x10C, 0x13C, 0x1C])
+@pytest.mark.parametrize("col,mag", [(640, 150.0), (643, 150.0), (640, 1500.0), (643, 1500.0), (130, 40.0), (1023, 800.0)])
+def test_attention_outlier_key_beyond_the_kept_reference(variant, col, mag):
+    """One key whose score exceeds everything before it by far more than 2^30 (in a polynomial-exp column, col % 8 < 2,
+    or a MUFU column): the optimistic-reference kernel must notice (row-sum / polynomial-argument guard) and redo the
+    block with the true row maximum; rows anti-aligned with the key see a hugely negative score instead."""
+    from easyanimate_b200 import ops
+    B, H, S = 1, 2, 1100
+    g = torch.Generator(device="cuda").manual_seed(11)
+    u = torch.nn.functional.normalize(torch.randn(64, device="cuda", generator=g), dim=0)
+    q = torch.randn(B, H, S, 64, device="cuda", generator=g) + 3.0 * u
+    k = torch.randn(B, H, S, 64, device="cuda", generator=g)
+    k[:, :, col] = mag * u
+    v = torch.randn(B, H, S, 64, device="cuda", generator=g)
+    q, k, v = q.to(bf16), k.to(bf16), v.to(bf16)
+    ref = _ref(q, k, v)
+    ot, ov = ops.attention(q, k, v, 0, variant=variant)
+    assert torch.isfinite(ov).all()
+    torch.testing.assert_close(ov.float(), ref, rtol=3e-2, atol=2e-2)
