@@ -364,6 +364,7 @@ int launch_attn3(const ea_attn_args* g, int poly, cudaStream_t stream);
 int launch_attn4(const ea_attn_args* g, int poly, cudaStream_t stream);
 int launch_attn5(const ea_attn_args* g, int poly, cudaStream_t stream);
 int launch_attn6(const ea_attn_args* g, int poly, cudaStream_t stream);
+int launch_attn7(const ea_attn_args* g, int poly, cudaStream_t stream);
 }
 using namespace ea;
 
@@ -376,6 +377,7 @@ extern "C" int ea_attn_fwd(const ea_attn_args* g, void* stream_) {
   EA_REQUIRE(g->S_text == 0 || g->out_text, "ea_attn_fwd: out_text missing");
   EA_REQUIRE(g->S_text == g->S || g->out_video, "ea_attn_fwd: out_video missing");
   EA_REQUIRE(g->B * g->H <= 65535, "ea_attn_fwd: B*H exceeds grid.y");
+  if (g->variant & 0x200) return ea::launch_attn7(g, (g->variant >> 4) & 7, stream);  // optimistic reference + column split
   if (g->variant & 0x100) return ea::launch_attn6(g, (g->variant >> 4) & 7, stream);  // optimistic reference, no hot-path row max
   if (g->variant & 0x80) return ea::launch_attn5(g, (g->variant >> 4) & 7, stream);  // column-split softmax, 16 softmax warps
   if ((g->variant & 12) == 12) return ea::launch_attn4(g, (g->variant >> 4) & 7, stream);  // one-pass two-tile kernel
