@@ -305,9 +305,14 @@ def main():
                     "d2h_bytes_per_step": out_host.numel() * 2},
             "gpu_launches": int(launches),
             "clocks": clock_info,
-            "roofline": {"kernel": "attn_fwd_kernel (joint text+video attention, hd=64)", "bound": "tensor",
+            "roofline": {"kernel": "a6::attn6_kernel (joint text+video attention, hd=64, ea_attn_args.variant 0x%x)" % ops.ATTN_VARIANT, "bound": "tensor",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
-                         "peak_source": peak_src + " (of measured)", "traffic": None,
+                         "peak_source": peak_src + " (of measured)",
+                         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the ncu --set full capture of
+                         # this kernel on this shape (profiles/r01_ncu_attn_v6_step_summary.txt: 2.3135 GB at B=2, i.e.
+                         # exactly Q+K+V+O once); not re-measured live
+                         "traffic": (1.746926e9 + 0.566597e9) * B_attn / 2 if args.preset == "R720_7B" else None,
+                         "traffic_algorithmic": 4.0 * B_attn * preset["heads"] * S * 64 * 2,
                          "launches_timed": len(attn_ms), "avg_ms": attn_avg_ms, "flops_per_launch": attn_flops,
                          "share_of_step": (sum(attn_ms) / ms_total) if attn_ms else None},
         }

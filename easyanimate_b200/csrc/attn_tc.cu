@@ -359,12 +359,9 @@ static int launch_attn(const ea_attn_args* g, cudaStream_t stream) {
 }  // namespace ea
 
 namespace ea {
-int launch_attn2(const ea_attn_args* g, int poly, cudaStream_t stream);
-int launch_attn3(const ea_attn_args* g, int poly, cudaStream_t stream);
 int launch_attn4(const ea_attn_args* g, int poly, cudaStream_t stream);
-int launch_attn5(const ea_attn_args* g, int poly, cudaStream_t stream);
 int launch_attn6(const ea_attn_args* g, int poly, cudaStream_t stream);
-int launch_attn7(const ea_attn_args* g, int poly, cudaStream_t stream);
+int launch_attn9(const ea_attn_args* g, int poly, cudaStream_t stream);
 }
 using namespace ea;
 
@@ -377,12 +374,10 @@ extern "C" int ea_attn_fwd(const ea_attn_args* g, void* stream_) {
   EA_REQUIRE(g->S_text == 0 || g->out_text, "ea_attn_fwd: out_text missing");
   EA_REQUIRE(g->S_text == g->S || g->out_video, "ea_attn_fwd: out_video missing");
   EA_REQUIRE(g->B * g->H <= 65535, "ea_attn_fwd: B*H exceeds grid.y");
-  if (g->variant & 0x200) return ea::launch_attn7(g, (g->variant >> 4) & 7, stream);  // optimistic reference + column split
-  if (g->variant & 0x100) return ea::launch_attn6(g, (g->variant >> 4) & 7, stream);  // optimistic reference, no hot-path row max
-  if (g->variant & 0x80) return ea::launch_attn5(g, (g->variant >> 4) & 7, stream);  // column-split softmax, 16 softmax warps
-  if ((g->variant & 12) == 12) return ea::launch_attn4(g, (g->variant >> 4) & 7, stream);  // one-pass two-tile kernel
-  if (g->variant & 8) return ea::launch_attn3(g, (g->variant >> 4) & 7, stream);  // two tiles, double-buffered S
-  if (g->variant & 4) return ea::launch_attn2(g, (g->variant >> 4) & 7, stream);  // two-tile ping-pong kernel
+  if (g->variant & 0x1000) return ea::launch_attn9(g, (g->variant >> 4) & 7, stream);  // tensor-core row sums, truncated P
+  if (g->variant & 0x100) return ea::launch_attn6(g, (g->variant >> 4) & 7, stream);   // optimistic reference (default)
+  if ((g->variant & 12) == 12) return ea::launch_attn4(g, (g->variant >> 4) & 7, stream);  // per-block row maximum
+  EA_REQUIRE((g->variant & ~3) == 0, "ea_attn_fwd: unknown kernel variant");
   const bool vt = (g->variant & 2) != 0, pt = (g->variant & 1) != 0;
   if (vt) EA_REQUIRE(g->S_pad >= g->S && g->S_pad % 8 == 0, "ea_attn_fwd: S_pad must be >= S and a multiple of 8");
   if (!pt && !vt) return launch_attn<false, false>(g, stream);

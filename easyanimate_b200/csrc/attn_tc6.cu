@@ -41,6 +41,7 @@ struct Args {
   bf16* out_video;
   int B, H, S, S_text;
   float scale_log2;
+  uint32_t dep_zero;  // always 0; a value the compiler cannot see through (exp_row_phased)
 };
 
 struct Smem {
@@ -129,9 +130,18 @@ EA_DEVICE void tmem_ld_fence(uint32_t* r) {
                : "memory");
 }
 
+// fp32 pair -> packed bf16x2.  RN uses F2FP, which issues at 1 per 4 cycles per sub-partition (profiles/
+// r01_issue_mix_microbench.log); TRUNC keeps the high halves with one PRMT (the mean truncation loss of bf16, 2^-8.47,
+// is compensated once, in the epilogue).
+template <bool TRUNC>
+EA_DEVICE uint32_t pack_p(float lo, float hi) {
+  if constexpr (TRUNC) return __byte_perm(__float_as_uint(lo), __float_as_uint(hi), 0x7632);
+  else return pack_bf16x2(lo, hi);
+}
+
 // Column pairs [P0, P1) of one 32-column chunk: e = 2^(s * c - m) with packed fp32x2 arithmetic, POLY of every 4 pairs on
 // the FMA pipe (their raw scores also feed `guard`), the rest on MUFU; row-sum partials in acc2, packed bf16 pairs in pk.
-template <int POLY, int P0, int P1>
+template <int POLY, int P0, int P1, bool TRUNC = false>
 EA_DEVICE void exp_pairs(const uint32_t* s, float2 c2, float2 nm2, float2* acc2, float& guard, uint32_t* pk) {
 #pragma unroll
   for (int q = P0; q < P1; ++q) {
@@ -146,11 +156,45 @@ EA_DEVICE void exp_pairs(const uint32_t* s, float2 c2, float2 nm2, float2* acc2,
       e.y = ex2(x.y);
     }
     acc2[q & 3] = __fadd2_rn(acc2[q & 3], e);
-    pk[q] = pack_bf16x2(e.x, e.y);
+    pk[q] = pack_p<TRUNC>(e.x, e.y);
   }
 }
 
+// The same over a whole 128-column row, but in two PHASES: first every polynomial pair, then every MUFU pair.  A warp
+// stalled at the MUFU queue cannot issue the FMA work queued behind it (in order), so mixing the two kinds pair by pair
+// leaves both pipes half idle; with phases, one tile's FMA-only phase runs under the other tile's MUFU phase (the two
+// softmax warps of a sub-partition belong to different tiles).  `dep_zero` is a runtime zero that chains the MUFU
+// phase's inputs to the last polynomial result so that ptxas cannot merge the phases back together.
 template <int POLY>
+EA_DEVICE void exp_row_phased(const uint32_t* s, float2 c2, float2 nm2, float2* acc2, float& guard, uint32_t* pk,
+                              uint32_t dep_zero) {
+  uint32_t last = 0;
+#pragma unroll
+  for (int q = 0; q < 64; ++q) {
+    if ((q & 3) < POLY) {
+      const float s0 = __uint_as_float(s[2 * q]), s1 = __uint_as_float(s[2 * q + 1]);
+      guard = fmaxf(guard, fmaxf(s0, s1));
+      const float2 e = exp2_poly2(__ffma2_rn(make_float2(s0, s1), c2, nm2));
+      acc2[q & 3] = __fadd2_rn(acc2[q & 3], e);
+      pk[q] = pack_bf16x2(e.x, e.y);
+      last = pk[q];
+    }
+  }
+  const float2 nm2b = make_float2(__uint_as_float(__float_as_uint(nm2.x) | (last & dep_zero)), nm2.y);
+#pragma unroll
+  for (int q = 0; q < 64; ++q) {
+    if ((q & 3) >= POLY) {
+      const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[2 * q]), __uint_as_float(s[2 * q + 1])), c2, nm2b);
+      float2 e;
+      e.x = ex2(x.x);
+      e.y = ex2(x.y);
+      acc2[q & 3] = __fadd2_rn(acc2[q & 3], e);
+      pk[q] = pack_bf16x2(e.x, e.y);
+    }
+  }
+}
+
+template <int POLY, bool PHASED, bool TRUNC>
 __global__ void __launch_bounds__(kThreads, 1)
 attn6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
              const __grid_constant__ CUtensorMap tmap_v, const Args p) {
@@ -307,27 +351,48 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         // ---- fast pass: exponentiate against the reference kept from earlier blocks.  The P stores trail the
         // exponentials by one chunk so that the wait for PV_{j-1} (which reads P_t) sits in the middle of the block.
         const float2 nm2 = make_float2(-m_ref, -m_ref);
-        tmem_ld32p(tS, s);
-        tmem_ld_fence(s);
-        tmem_ld32p(tS + 32, s + 32);
-        exp_pairs<POLY, 0, 16>(s, c2, nm2, acc2, guard, pk);
-        tmem_ld_fence(s + 32);
-        tmem_ld32p(tS + 64, s + 64);
-        exp_pairs<POLY, 0, 8>(s + 32, c2, nm2, acc2, guard, pk2);
-        tmem_ld_fence(s + 64);
-        tmem_ld32p(tS + 96, s + 96);
-        exp_pairs<POLY, 8, 16>(s + 32, c2, nm2, acc2, guard, pk2);
-        tmem_ld_fence(s + 96);
-        tc_fence_before();
-        bar_arrive(bar_t + kSFree);  // S_t may be overwritten by QK_{j+1}
-        bar_wait(bar_t + kODone, (j - 1) & 1);  // PV_{j-1} has read P_t
-        tc_fence_after();
-        tmem_st16(tP, pk);
-        tmem_st16(tP + 16, pk2);
-        exp_pairs<POLY, 0, 16>(s + 64, c2, nm2, acc2, guard, pk);
-        tmem_st16(tP + 32, pk);
-        exp_pairs<POLY, 0, 16>(s + 96, c2, nm2, acc2, guard, pk2);
-        tmem_st16(tP + 48, pk2);
+        if constexpr (PHASED) {
+          uint32_t pkr[64];
+          tmem_ld32p(tS, s);
+          tmem_ld32p(tS + 32, s + 32);
+          tmem_ld32p(tS + 64, s + 64);
+          tmem_ld32p(tS + 96, s + 96);
+          tmem_ld_fence(s);
+          tmem_ld_fence(s + 32);
+          tmem_ld_fence(s + 64);
+          tmem_ld_fence(s + 96);
+          tc_fence_before();
+          bar_arrive(bar_t + kSFree);  // S_t may be overwritten by QK_{j+1}
+          exp_row_phased<POLY>(s, c2, nm2, acc2, guard, pkr, p.dep_zero);
+          bar_wait(bar_t + kODone, (j - 1) & 1);  // PV_{j-1} has read P_t
+          tc_fence_after();
+          tmem_st16(tP, pkr);
+          tmem_st16(tP + 16, pkr + 16);
+          tmem_st16(tP + 32, pkr + 32);
+          tmem_st16(tP + 48, pkr + 48);
+        } else {
+          tmem_ld32p(tS, s);
+          tmem_ld_fence(s);
+          tmem_ld32p(tS + 32, s + 32);
+          exp_pairs<POLY, 0, 16, TRUNC>(s, c2, nm2, acc2, guard, pk);
+          tmem_ld_fence(s + 32);
+          tmem_ld32p(tS + 64, s + 64);
+          exp_pairs<POLY, 0, 8, TRUNC>(s + 32, c2, nm2, acc2, guard, pk2);
+          tmem_ld_fence(s + 64);
+          tmem_ld32p(tS + 96, s + 96);
+          exp_pairs<POLY, 8, 16, TRUNC>(s + 32, c2, nm2, acc2, guard, pk2);
+          tmem_ld_fence(s + 96);
+          tc_fence_before();
+          bar_arrive(bar_t + kSFree);  // S_t may be overwritten by QK_{j+1}
+          bar_wait(bar_t + kODone, (j - 1) & 1);  // PV_{j-1} has read P_t
+          tc_fence_after();
+          tmem_st16(tP, pk);
+          tmem_st16(tP + 16, pk2);
+          exp_pairs<POLY, 0, 16, TRUNC>(s + 64, c2, nm2, acc2, guard, pk);
+          tmem_st16(tP + 32, pk);
+          exp_pairs<POLY, 0, 16, TRUNC>(s + 96, c2, nm2, acc2, guard, pk2);
+          tmem_st16(tP + 48, pk2);
+        }
         const float l_blk = ((acc2[0].x + acc2[0].y) + (acc2[1].x + acc2[1].y)) + ((acc2[2].x + acc2[2].y) + (acc2[3].x + acc2[3].y));
         const bool ok = (l_blk <= 1073741824.0f) && (POLY == 0 || fmaf(guard, p.scale_log2, -m_ref) <= 64.0f);
         redo = __any_sync(0xffffffffu, !ok);
@@ -379,7 +444,7 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           // (rare path: keep it small - rotate the score registers instead of unrolling four copies)
-          exp_pairs<POLY, 0, 16>(s, c2, nm2, acc2, guard, pk);
+          exp_pairs<POLY, 0, 16, TRUNC>(s, c2, nm2, acc2, guard, pk);
           tmem_st16(tP + c * 16, pk);
 #pragma unroll
           for (int i = 0; i < 96; ++i) s[i] = s[i + 32];
@@ -392,7 +457,7 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     }
     bar_wait(bar_t + kODone, (nblk - 1) & 1);
     tc_fence_after();
-    const float inv_l = 1.0f / l;
+    const float inv_l = (TRUNC ? 1.00282f : 1.0f) / l;
     const int srow = q0 + t * kQT + r;
     bf16* dst = nullptr;
     if (srow < p.S) {
@@ -432,7 +497,7 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
   }
 }
 
-template <int POLY>
+template <int POLY, bool PHASED, bool TRUNC>
 static int launch(const ea_attn_args* g, cudaStream_t stream) {
   const int64_t BH = g->B * g->H;
   CUtensorMap tq, tk, tv;
@@ -451,7 +516,8 @@ static int launch(const ea_attn_args* g, cudaStream_t stream) {
   p.out_video = reinterpret_cast<bf16*>(g->out_video);
   p.B = (int)g->B; p.H = (int)g->H; p.S = (int)g->S; p.S_text = (int)g->S_text;
   p.scale_log2 = g->scale * 1.4426950408889634f;
-  auto kern = attn6_kernel<POLY>;
+  p.dep_zero = 0;
+  auto kern = attn6_kernel<POLY, PHASED, TRUNC>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kTotal);
@@ -467,13 +533,15 @@ static int launch(const ea_attn_args* g, cudaStream_t stream) {
 }  // namespace a6
 
 int launch_attn6(const ea_attn_args* g, int poly, cudaStream_t stream) {
+  const bool trunc = (g->variant & 0x800) != 0;  // experimental: P by truncation (PRMT) instead of F2FP round-to-nearest
   switch (poly) {
-    case 0: return a6::launch<0>(g, stream);
-    case 1: return a6::launch<1>(g, stream);
-    case 2: return a6::launch<2>(g, stream);
-    case 3: return a6::launch<3>(g, stream);
-    case 4: return a6::launch<4>(g, stream);
-    default: return fail(EA_ERR_INVALID, "ea_attn_fwd: unsupported polynomial fraction (0..4 of every 8)");
+    case 0: return trunc ? a6::launch<0, false, true>(g, stream) : a6::launch<0, false, false>(g, stream);
+    case 1: return trunc ? a6::launch<1, false, true>(g, stream) : a6::launch<1, false, false>(g, stream);
+    case 2: return trunc ? a6::launch<2, false, true>(g, stream) : a6::launch<2, false, false>(g, stream);
+    case 3: return a6::launch<3, false, false>(g, stream);
+    case 5: return a6::launch<1, true, false>(g, stream);  // polynomial pairs first, then the MUFU pairs (two phases)
+    case 6: return a6::launch<2, true, false>(g, stream);
+    default: return fail(EA_ERR_INVALID, "ea_attn_fwd: unsupported polynomial fraction (0..3 of every 4 pairs; 5, 6: phased 1, 2)");
   }
 }
 

@@ -1,0 +1,505 @@
+// Joint text+video attention forward, ninth generation (A/B variant 0x100c, NOT the default): the sixth generation
+// (attn_tc6.cu) with the softmax's non-MUFU instruction budget cut in half.  Measured: correct, but 775 TFLOP/s against the
+// sixth generation's 883 - the seven extra 16-column row-sum MMAs per block cost ~10 %, and inside the pipeline the
+// polynomial still does not pay although the isolated loop (tools/microbench/softmax_mix_bench.cu) says it should
+// (1 494 vs 1 880 cycles per block pair): DESIGN.md section 5.  Kept because the technique (row sums from the tensor
+// core, exact normalisation of truncated weights) and its numbers are what the next round starts from.
+//
+// What tools/microbench/issue_mix_bench.cu measured on a B200 sub-partition (profiles/r01_issue_mix_microbench.log):
+// MUFU.EX2 issues every 8 cycles, packed FFMA2/FADD2 every 2, F2FP (fp32 pair -> bf16x2) only every 4, scalar FMA/ALU
+// ~1-1.2; MUFU overlaps with everything else, but FMA, ALU and conversion instructions share what behaves like ONE port.
+// Per 128-key block and softmax warp the sixth generation therefore needs 1024 XU cycles and 653 "other" cycles (64
+// FFMA2 = 128, 64 FADD2 = 128, 64 F2FP = 256, ~140 bookkeeping): XU-bound, and each polynomial pair (17.7 "other"
+// cycles for 16 XU cycles saved) tips it into "other"-bound - which is why every polynomial variant measured slower.
+// Here:
+//   * P is packed by TRUNCATION (one PRMT per pair instead of F2FP) and the row sum l comes from the TENSOR CORE
+//     (a second, 16-column MMA of the same P against an all-ones tile), so O and l are accumulated from the very same
+//     bf16 weights: the normalisation is exact for the weights used, no rounding bias, and the 64 FADD2 disappear;
+//   * the end-of-block overflow verdict (attn_tc6.cu) no longer has a row sum to look at: exponentials are computed
+//     2^-16 low (reference = m_ref + 16, floating point: no precision change) and the verdict is "some packed P has
+//     exponent bit 7 set" (>= 2.0, inf or NaN, i.e. the row maximum grew by more than 2^17 relative to the reference):
+//     one 3-input LOP3 per two pairs; polynomial columns are guarded by their raw maximum as before;
+//   * key blocks are 112 keys so that the extra accumulator fits in TMEM:
+//       S_t at 112 t | P_t (packed bf16, 56 columns) at 224 + 64 t | O_t at 352 + 64 t | L_t (16 columns) at 480 + 16 t
+//   "other" per 112-key block: 56 FFMA2 + 56 PRMT + 28 LOP3 + bookkeeping = ~370 cycles against 896 XU cycles, which
+//   leaves room for POLY8 of every 8 column pairs on the FMA pipe.
+//
+//   warps 0-3 / 4-7 : softmax of tile A / B, one query row per thread (setmaxnreg 232)
+//   warp 8          : TMA producer (Q once, K_j / V_j 112-key tiles through 4-stage rings)
+//   warps 9 / 10    : MMA issuer of tile A / B (9 also owns the TMEM allocation);  warp 11: fills the all-ones tile
+#include "common.cuh"
+#include "host.h"
+#include "../../include/ea_b200.h"
+
+namespace ea {
+
+extern void count_launch();
+
+namespace a9 {
+
+constexpr int kThreads = 384;
+constexpr int kQT = 128;
+constexpr int kKT = 112;
+constexpr int kHD = 64;
+constexpr int kStages = 4;
+constexpr int kPairs = kKT / 2;  // 56 column pairs per row and block
+constexpr float kShift = 16.0f;  // exponentials are computed 2^-16 low (see the verdict)
+
+struct Args {
+  bf16* out_text;
+  bf16* out_video;
+  int B, H, S, S_text;
+  float scale_log2;
+};
+
+struct Smem {
+  static constexpr int kQBytes = 2 * kQT * kHD * 2;
+  static constexpr int kKBytes = kKT * kHD * 2;  // 14 336 = 14 swizzle groups of 1 024 B
+  static constexpr int kVBytes = kKT * kHD * 2;
+  static constexpr int kOnesBytes = 2048;        // 16 keys x 128 B of bf16 1.0 (the B operand of the row-sum MMA)
+  static constexpr int kOffQ = 0;
+  static constexpr int kOffK = kOffQ + kQBytes;
+  static constexpr int kOffV = kOffK + kStages * kKBytes;
+  static constexpr int kOffOnes = kOffV + kStages * kVBytes;
+  static constexpr int kOffBar = kOffOnes + kOnesBytes;
+  static constexpr int kTotal = kOffBar + 512 + 1024;
+};
+
+constexpr uint32_t kColS = 0, kColP = 224, kColO = 352, kColL = 480;
+constexpr uint32_t kTmemCols = 512;
+
+EA_DEVICE void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+EA_DEVICE void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+EA_DEVICE void tmem_ld32p(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+EA_DEVICE void tmem_ld16p(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// tcgen05.wait::ld that also "touches" destination registers of the loads it completes, so that the compiler cannot
+// schedule their first use above the wait
+EA_DEVICE void tmem_ld_fence32(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+EA_DEVICE void tmem_ld_fence16(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+EA_DEVICE float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 2^x for a column pair on the FMA/ALU pipes: x = n + f (round to nearest), degree-3 minimax 2^f, exponent add.
+// Valid for -126 <= x < 128 (clamped below here; the caller guards the upper side).
+EA_DEVICE float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 y = __fadd2_rn(x, make_float2(12582912.0f, 12582912.0f));
+  const float2 n = __fadd2_rn(y, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = __ffma2_rn(n, make_float2(-1.0f, -1.0f), x);
+  float2 q = __ffma2_rn(f, make_float2(0.05500892f, 0.05500892f), make_float2(0.24221097f, 0.24221097f));
+  q = __ffma2_rn(q, f, make_float2(0.69328290f, 0.69328290f));
+  q = __ffma2_rn(q, f, make_float2(1.0f, 1.0f));
+  float2 e;
+  e.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(y.x) << 23));
+  e.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(y.y) << 23));
+  return e;
+}
+// Hot-loop mbarrier operations on precomputed 32-bit shared addresses (see attn_tc6.cu)
+EA_DEVICE uint32_t opaque(uint32_t x) {
+  asm volatile("" : "+r"(x));
+  return x;
+}
+EA_DEVICE void bar_wait(uint32_t addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
+EA_DEVICE void bar_arrive(uint32_t addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+
+// One row's 56 column pairs: e = 2^(s * c - (m_ref + 16)), POLY8 of every 8 pairs on the FMA pipe (their raw scores also
+// feed `guard`), the rest on MUFU; P by truncation; `orw` collects every packed word for the overflow verdict.
+template <int POLY8>
+EA_DEVICE void exp_row(const uint32_t* s, float2 c2, float2 nm2, float& guard, uint32_t* pk, uint32_t& orw) {
+#pragma unroll
+  for (int q = 0; q < kPairs; ++q) {
+    const float s0 = __uint_as_float(s[2 * q]), s1 = __uint_as_float(s[2 * q + 1]);
+    const float2 x = __ffma2_rn(make_float2(s0, s1), c2, nm2);
+    float2 e;
+    if ((q & 7) < POLY8) {
+      guard = fmaxf(guard, fmaxf(s0, s1));
+      e = exp2_poly2(x);
+    } else {
+      e.x = ex2(x.x);
+      e.y = ex2(x.y);
+    }
+    pk[q] = __byte_perm(__float_as_uint(e.x), __float_as_uint(e.y), 0x7632);  // {bf16 trunc(e.y), bf16 trunc(e.x)}
+    orw |= pk[q];
+  }
+}
+
+template <int POLY8>
+__global__ void __launch_bounds__(kThreads, 1)
+attn9_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+             const __grid_constant__ CUtensorMap tmap_v, const Args p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + Smem::kOffQ;
+  uint8_t* sK = smem + Smem::kOffK;
+  uint8_t* sV = smem + Smem::kOffV;
+  uint8_t* sOnes = smem + Smem::kOffOnes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::kOffBar);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = k_full + kStages;
+  uint64_t* v_full = k_empty + kStages;
+  uint64_t* v_empty = v_full + kStages;
+  uint64_t* s_full = v_empty + kStages;   // [tile]
+  uint64_t* s_free = s_full + 2;          // [tile]
+  uint64_t* p_ready = s_free + 2;         // [tile]
+  uint64_t* o_done = p_ready + 2;         // [tile]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (2 * kQT);
+  const int bh = blockIdx.y;
+  const int nblk = (p.S + kKT - 1) / kKT;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 2);  // one tcgen05.commit per tile issuer
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 2);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 128);
+      mbar_init(&p_ready[i], 128);
+      mbar_init(&o_done[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 11) {
+    // the all-ones B operand of the row-sum MMA (every element is 1.0, so its swizzle does not matter)
+    for (int i = lane; i < Smem::kOnesBytes / 4; i += 32) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3f803f80u;
+    fence_proxy_async_smem();
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 8) {
+    // ---- producer / MMA warpgroup: give registers back
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 8) {
+      if (lane == 0) {
+        // ===== TMA producer =====
+        mbar_arrive_expect_tx(q_full, Smem::kQBytes);
+        tma_load_3d(sQ, &tmap_q, q_full, 0, q0, bh);
+        int st = 0;
+        uint32_t ph = 0;
+        for (int j = 0; j < nblk; ++j) {
+          mbar_wait(&k_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&k_full[st], Smem::kKBytes);
+          tma_load_3d(sK + st * Smem::kKBytes, &tmap_k, &k_full[st], 0, j * kKT, bh);
+          mbar_wait(&v_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&v_full[st], Smem::kVBytes);
+          tma_load_3d(sV + st * Smem::kVBytes, &tmap_v, &v_full[st], 0, j * kKT, bh);
+          if (++st == kStages) { st = 0; ph ^= 1; }
+        }
+      }
+    } else if (warp <= 10) {
+      if (lane == 0) {
+        // ===== MMA issuers: warp 9 drives tile A, warp 10 drives tile B, independently (see attn_tc4.cu) =====
+        const int t = warp - 9;
+        constexpr uint32_t idesc_qk = umma_idesc_bf16(kQT, kKT, 0, 0);
+        constexpr uint32_t idesc_pv = umma_idesc_bf16(kQT, kHD, 0, 1);  // V: MN-major B operand
+        constexpr uint32_t idesc_l = umma_idesc_bf16(kQT, 16, 0, 1);    // all-ones B operand, 16 identical columns
+        mbar_wait(q_full, 0);
+        tc_fence_after();
+        const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ + t * (kQT * kHD * 2)));
+        const uint64_t onesdesc = umma_desc_sw128_mn(smem_u32(sOnes), 16384, 1024);
+        auto issue_qk = [&](int j) {
+          const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + (j % kStages) * Smem::kKBytes));
+          const uint32_t d = tmem_base + kColS + t * kKT;
+#pragma unroll
+          for (int k = 0; k < kHD / 16; ++k) umma_ss(d, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+          umma_commit(&s_full[t]);
+        };
+        auto issue_pv = [&](int j) {
+          const uint32_t vaddr = smem_u32(sV + (j % kStages) * Smem::kVBytes);
+          const uint32_t d = tmem_base + kColO + t * kHD;
+          const uint32_t dl = tmem_base + kColL + t * 16;
+          const uint32_t pa = tmem_base + kColP + t * 64;
+#pragma unroll
+          for (int k = 0; k < kKT / 16; ++k) {
+            umma_ts(d, pa + k * 8, umma_desc_sw128_mn(vaddr + k * 2048, 16384, 1024), idesc_pv, (j | k) != 0);
+            umma_ts(dl, pa + k * 8, onesdesc, idesc_l, (j | k) != 0);  // L_t += P_t[:, 16k..16k+15] * 1
+          }
+          umma_commit(&o_done[t]);
+        };
+        mbar_wait(&k_full[0], 0);
+        tc_fence_after();
+        issue_qk(0);
+        umma_commit(&k_empty[0]);  // K/V stages are released when BOTH issuers have committed (barrier count 2)
+        for (int j = 0; j < nblk; ++j) {
+          const int st = j % kStages;
+          const uint32_t par = j & 1;
+          if (j + 1 < nblk) {
+            mbar_wait(&s_free[t], par);  // this tile's softmax has pulled S(j) into registers
+            mbar_wait(&k_full[(j + 1) % kStages], ((j + 1) / kStages) & 1);
+            tc_fence_after();
+            issue_qk(j + 1);
+            umma_commit(&k_empty[(j + 1) % kStages]);
+          }
+          mbar_wait(&p_ready[t], par);
+          mbar_wait(&v_full[st], (j / kStages) & 1);
+          tc_fence_after();
+          issue_pv(j);
+          umma_commit(&v_empty[st]);
+        }
+      }
+    }
+  } else {
+    // ---- softmax warpgroups: take the registers (256 x 232 + 128 x 40 = 384 x 168, the launch allocation)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int t = warp >> 2;
+    const int ew = warp & 3;
+    const int r = ew * 32 + lane;
+    const uint32_t lane_off = uint32_t(ew * 32) << 16;
+    const uint32_t tS = tmem_base + lane_off + kColS + t * kKT;
+    const uint32_t tP = tmem_base + lane_off + kColP + t * 64;
+    const uint32_t tO = tmem_base + lane_off + kColO + t * kHD;
+    const uint32_t tL = tmem_base + lane_off + kColL + t * 16;
+    const uint32_t bar_t = opaque(smem_u32(&s_full[t]));  // s_full[t]; s_free[t] +16, p_ready[t] +32, o_done[t] +48
+    constexpr uint32_t kSFree = 16, kPReady = 32, kODone = 48;
+    float m_ref = 0.f;
+    const float2 c2 = make_float2(p.scale_log2, p.scale_log2);
+    for (int j = 0; j < nblk; ++j) {
+      bar_wait(bar_t, j & 1);
+      // start the two tiles half a period apart (see attn_tc4.cu)
+      if (t == 1 && j == 0) mbar_wait(&s_free[0], 0);
+      tc_fence_after();
+      uint32_t s[kKT];
+      uint32_t pk[kPairs];
+      const int valid = p.S - j * kKT;  // < 112 only in the last block (TMA zero-filled the missing keys)
+      tmem_ld32p(tS, s);
+      tmem_ld32p(tS + 32, s + 32);
+      tmem_ld32p(tS + 64, s + 64);
+      tmem_ld16p(tS + 96, s + 96);
+      tmem_ld_fence32(s);
+      tmem_ld_fence32(s + 32);
+      tmem_ld_fence32(s + 64);
+      tmem_ld_fence16(s + 96);
+      tc_fence_before();
+      bar_arrive(bar_t + kSFree);  // S_t may be overwritten by QK_{j+1}
+      bool redo = (j == 0) || (valid < kKT);
+      if (!redo) {
+        // ---- fast pass: exponentiate against the reference kept from earlier blocks, verdict afterwards
+        const float2 nm2 = make_float2(-(m_ref + kShift), -(m_ref + kShift));
+        float guard = -INFINITY;
+        uint32_t orw = 0;
+        exp_row<POLY8>(s, c2, nm2, guard, pk, orw);
+        bar_wait(bar_t + kODone, (j - 1) & 1);  // PV_{j-1} has read P_t
+        tc_fence_after();
+        tmem_st16(tP, pk);
+        tmem_st16(tP + 16, pk + 16);
+        tmem_st16(tP + 32, pk + 32);
+        tmem_st8(tP + 48, pk + 48);
+        const bool ok = ((orw & 0x40004000u) == 0) && (POLY8 == 0 || fmaf(guard, p.scale_log2, -m_ref) <= 64.0f);
+        redo = __any_sync(0xffffffffu, !ok);
+      } else if (valid < kKT) {
+#pragma unroll
+        for (int i = 0; i < kKT; ++i)
+          if (i >= valid) s[i] = 0xff800000u;  // -inf
+      }
+      if (redo) {
+        // ---- classic pass from the registers: true row maximum, rescale O_t and L_t, exponentiate again (block 0, a
+        // ragged last block, or a row whose scores outgrew the reference by more than 2^17)
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < kKT; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(s[i]));
+        const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
+        if (j == 0) {
+          m_ref = mx;
+        } else {
+          bar_wait(bar_t + kODone, (j - 1) & 1);
+          tc_fence_after();
+          const float m_new = fmaxf(m_ref, mx);
+          const float f = ex2(m_ref - m_new);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld32p(tO + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+            tmem_st16(tO + c * 32, v);
+            tmem_st16(tO + c * 32 + 16, v + 16);
+          }
+          {
+            uint32_t v[16];
+            tmem_ld16p(tL, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+            tmem_st16(tL, v);
+          }
+          tmem_st_wait();
+          m_ref = m_new;
+        }
+        const float2 nm2 = make_float2(-(m_ref + kShift), -(m_ref + kShift));
+        float guard = -INFINITY;
+        uint32_t orw = 0;
+        exp_row<POLY8>(s, c2, nm2, guard, pk, orw);
+        tmem_st16(tP, pk);
+        tmem_st16(tP + 16, pk + 16);
+        tmem_st16(tP + 32, pk + 32);
+        tmem_st8(tP + 48, pk + 48);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      bar_arrive(bar_t + kPReady);
+    }
+    bar_wait(bar_t + kODone, (nblk - 1) & 1);
+    tc_fence_after();
+    uint32_t lv[16];
+    tmem_ld16p(tL, lv);
+    tmem_ld_wait();
+    const float inv_l = 1.0f / __uint_as_float(lv[0]);
+    const int srow = q0 + t * kQT + r;
+    bf16* dst = nullptr;
+    if (srow < p.S) {
+      const int bb = bh / p.H, h = bh % p.H;
+      const int64_t d = (int64_t)p.H * kHD;
+      if (srow < p.S_text)
+        dst = p.out_text + ((int64_t)bb * p.S_text + srow) * d + h * kHD;
+      else
+        dst = p.out_video + ((int64_t)bb * (p.S - p.S_text) + (srow - p.S_text)) * d + h * kHD;
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      __syncwarp();
+      tmem_ld32p(tO + c * 32, v);
+      tmem_ld_wait();
+      if (dst != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(v[i * 8 + 0]) * inv_l, __uint_as_float(v[i * 8 + 1]) * inv_l);
+          w.y = pack_bf16x2(__uint_as_float(v[i * 8 + 2]) * inv_l, __uint_as_float(v[i * 8 + 3]) * inv_l);
+          w.z = pack_bf16x2(__uint_as_float(v[i * 8 + 4]) * inv_l, __uint_as_float(v[i * 8 + 5]) * inv_l);
+          w.w = pack_bf16x2(__uint_as_float(v[i * 8 + 6]) * inv_l, __uint_as_float(v[i * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + c * 32 + i * 8) = w;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <int POLY8>
+static int launch(const ea_attn_args* g, cudaStream_t stream) {
+  const int64_t BH = g->B * g->H;
+  CUtensorMap tq, tk, tv;
+  uint64_t dims[3] = {(uint64_t)kHD, (uint64_t)g->S, (uint64_t)BH};
+  uint64_t strides[2] = {(uint64_t)kHD * 2, (uint64_t)g->S * kHD * 2};
+  uint32_t box_q[3] = {kHD, 2 * kQT, 1};
+  uint32_t box_kv[3] = {kHD, kKT, 1};
+  int rc = make_tmap_bf16(&tq, g->q, 3, dims, strides, box_q, true);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tk, g->k, 3, dims, strides, box_kv, true);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tv, g->v, 3, dims, strides, box_kv, true);
+  if (rc) return rc;
+  Args p{};
+  p.out_text = reinterpret_cast<bf16*>(g->out_text);
+  p.out_video = reinterpret_cast<bf16*>(g->out_video);
+  p.B = (int)g->B; p.H = (int)g->H; p.S = (int)g->S; p.S_text = (int)g->S_text;
+  p.scale_log2 = g->scale * 1.4426950408889634f;
+  auto kern = attn9_kernel<POLY8>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kTotal);
+    if (e != cudaSuccess) return fail(EA_ERR_CUDA, std::string("cudaFuncSetAttribute(attn9): ") + cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((g->S + 2 * kQT - 1) / (2 * kQT)), (unsigned)BH);
+  kern<<<grid, kThreads, Smem::kTotal, stream>>>(tq, tk, tv, p);
+  count_launch();
+  return check_launch("attn9_kernel");
+}
+
+}  // namespace a9
+
+int launch_attn9(const ea_attn_args* g, int poly, cudaStream_t stream) {
+  switch (poly) {
+    case 0: return a9::launch<0>(g, stream);
+    case 1: return a9::launch<1>(g, stream);
+    case 2: return a9::launch<2>(g, stream);
+    case 3: return a9::launch<3>(g, stream);
+    case 4: return a9::launch<4>(g, stream);
+    default: return fail(EA_ERR_INVALID, "ea_attn_fwd: unsupported polynomial fraction (0..4 of every 8 column pairs)");
+  }
+}
+
+}  // namespace ea

@@ -177,13 +177,15 @@ int ea_ew_addsub(const void* a, const void* b, void* out, int64_t n, int32_t sub
  * q,k,v: [B,H,S,64] bf16 contiguous.  Output is token-major and split at S_text:
  * out_text[B,S_text,H*64], out_video[B,S-S_text,H*64].
  * variant selects the kernel generation (all produce the same softmax; kept for A/B measurements, profiles/):
- *   bit8 (0x100, the Python layer's default is 0x10c): sixth generation - two query tiles per CTA, one TMEM pass,
- *     exponentials against the reference kept from earlier key blocks with an end-of-block overflow check instead of
- *     a per-block row maximum;  bit7 (0x80): fifth generation - score columns split over two warps (16 softmax warps);
- *   bits 2+3 (0x0c): fourth generation (per-block row maximum, lazy rescale);  bit3 / bit2 alone: third / second;
- *   bits 4-6: how many of every 4 column pairs are exponentiated by a polynomial on the FMA pipe instead of MUFU;
- *   none of bits 2,3,7,8: first-generation one-tile kernel - bit0: P operand through TMEM instead of shared memory,
- *   bit1: v is pre-transposed [B,H,64,S_pad] (see ea_transpose_v). */
+ *   bit8 (0x100; the Python layer's default is 0x10c): sixth generation - two query tiles per CTA, one TMEM pass,
+ *     exponentials against the reference kept from earlier key blocks with an end-of-block overflow verdict instead of
+ *     a per-block row maximum; bits 4-6: 0-3 = that many of every 4 column pairs by a polynomial on the FMA pipe instead
+ *     of MUFU, 5/6 = 1/2 of 4 in two phases; bit11 (0x800): P packed by truncation instead of round-to-nearest;
+ *   bit12 (0x1000): ninth generation - row sums from the tensor core, truncated P, 112-key blocks, bits 4-6 = 0-4 of
+ *     every 8 pairs by polynomial;
+ *   bits 2+3 (0x0c): fourth generation (per-block row maximum, lazy rescale), bits 4-6 = 0-4 polynomial pairs of 4;
+ *   none of those: first-generation one-tile kernel - bit0: P operand through TMEM instead of shared memory,
+ *   bit1: v is pre-transposed [B,H,64,S_pad] (see ea_transpose_v).  Anything else is EA_ERR_INVALID. */
 typedef struct {
   const void* q;
   const void* k;

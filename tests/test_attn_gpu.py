@@ -5,11 +5,11 @@ import torch
 pytestmark = pytest.mark.gpu
 bf16 = torch.bfloat16
 
-# 0x1c: default (one-pass two-tile kernel, 1 of 4 column pairs by polynomial); 0x0c: all MUFU; 0x3c: 3 of 4 pairs by
-# polynomial; 1: first generation; 0x24 / 0x28: second / third generation
-# 0x9c / 0x8c: column-split softmax (16 softmax warps); 0x10c (default) / 0x11c / 0x12c: optimistic reference (no
-# hot-path row max); 0x20c / 0x21c: optimistic reference + column split
-VARIANTS = [0x10C, 0x11C, 0x12C, 0x20C, 0x21C, 0x1C, 0x0C, 0x3C, 0x9C, 0x8C, 0x1, 0x24, 0x28]
+# 0x10c: default - sixth generation (two query tiles per CTA, one TMEM pass, optimistic reference / end-of-block verdict,
+# all exponentials on MUFU); 0x11c / 0x12c: 1 / 2 of every 4 column pairs by the FMA-pipe polynomial; 0x15c / 0x16c: the
+# same in two phases; 0x90c: P by truncation; 0x100c-0x104c: ninth generation (tensor-core row sums, 112-key blocks,
+# 0..4 of 8 pairs by polynomial); 0x1c / 0x0c / 0x3c: fourth generation (per-block row maximum); 0-3: first generation
+VARIANTS = [0x10C, 0x11C, 0x12C, 0x15C, 0x16C, 0x90C, 0x100C, 0x101C, 0x102C, 0x104C, 0x1C, 0x0C, 0x3C, 0x1, 0x0, 0x3]
 SHAPES = [(1, 2, 128, 0), (1, 2, 256, 64), (2, 3, 1000, 77), (1, 4, 4176, 256), (1, 1, 8, 3), (2, 2, 300, 300)]
 
 
@@ -50,8 +50,8 @@ def test_attention_large_logits_and_running_max_rescale():
         torch.testing.assert_close(ov.float(), ref, rtol=3e-2, atol=2e-2)
 
 
-@pytest.mark.parametrize("variant", [0x11C, 0x10C, 0x13C, 0x20C, 0x21C, 0x1C])
-@pytest.mark.parametrize("col,mag", [(640, 150.0), (643, 150.0), (640, 1500.0), (643, 1500.0), (130, 40.0), (1023, 800.0)])
+@pytest.mark.parametrize("variant", [0x10C, 0x11C, 0x13C, 0x15C, 0x90C, 0x100C, 0x101C, 0x102C, 0x1C])
+@pytest.mark.parametrize("col,mag", [(640, 150.0), (643, 150.0), (640, 1500.0), (643, 1500.0), (130, 40.0), (1023, 800.0), (740, 1500.0), (700, 150.0)])
 def test_attention_outlier_key_beyond_the_kept_reference(variant, col, mag):
     """One key whose score exceeds everything before it by far more than 2^30 (in a polynomial-exp column, col % 8 < 2,
     or a MUFU column): the optimistic-reference kernel must notice (row-sum / polynomial-argument guard) and redo the

@@ -45,6 +45,8 @@ def bench_attn():
     shapes = [(1, 48, 13312 + 256, 256), (1, 48, 47056, 256)]
     if os.environ.get("EA_ATTN_SMALL"):
         shapes = [(1, 16, 8192 + 256, 256)]
+    if os.environ.get("EA_ATTN_SHAPE"):  # "B,H,S,S_text", e.g. the bench step's 2,48,47056,256
+        shapes = [tuple(int(x) for x in os.environ["EA_ATTN_SHAPE"].split(","))]
     for (B, H, S, St) in shapes:
         q = torch.randn(B, H, S, 64, device="cuda").to(bf16)
         k = torch.randn(B, H, S, 64, device="cuda").to(bf16)

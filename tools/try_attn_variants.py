@@ -18,7 +18,7 @@ for (B,H,S,St) in [(1,2,128,0),(1,2,256,64),(2,3,1000,77),(1,4,4096+80,256)]:
     err = (got-ref).abs().max().item()
     print("variant",variant,"shape",(B,H,S,St),"max_abs_err",round(err,5), "ref_absmax", round(ref.abs().max().item(),3), flush=True)
 ''' % ROOT
-VARIANTS = [int(v, 0) for v in os.environ.get('EA_VARIANTS', '1,4,0x24,0x34,0x44,0x54').split(',')]
+VARIANTS = [int(v, 0) for v in os.environ.get('EA_VARIANTS', '1,0x1c,0x10c,0x100c').split(',')]
 for variant in VARIANTS:
     try:
         r = subprocess.run([sys.executable, "-c", CODE, str(variant)], capture_output=True, text=True, timeout=120)
