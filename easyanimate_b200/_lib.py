@@ -120,7 +120,7 @@ ea_l1_sums = _sig("ea_l1_sums", [vp, vp, vp, i64, vp])
 ea_ew_addsub = _sig("ea_ew_addsub", [vp, vp, vp, i64, i32, vp])
 ea_conv3d_causal = _sig("ea_conv3d_causal", [C.POINTER(ConvArgs), vp])
 ea_vae_prepare_latents = _sig("ea_vae_prepare_latents", [vp, vp, vp, vp, i64, i64, i64, i64, i64, vp])
-ea_groupnorm_workspace = _sig("ea_groupnorm_workspace", [i64, i64], C.c_size_t)
+ea_groupnorm_workspace = _sig("ea_groupnorm_workspace", [i64, i64, i64], C.c_size_t)
 ea_groupnorm_stats = _sig("ea_groupnorm_stats", [vp, vp, vp, C.c_size_t, i64, i64, i64, i64, f32, vp])
 ea_groupnorm_apply = _sig("ea_groupnorm_apply", [vp, vp, vp, vp, vp, i64, i64, i64, i64, i32, vp])
 ea_upsample2x = _sig("ea_upsample2x", [vp, vp, i64, i64, i64, i64, vp])

@@ -38,11 +38,12 @@ __global__ void vae_prepare_latents_kernel(const bf16* __restrict__ z, const bf1
 }
 
 // ---- GroupNorm: per-frame statistics (common.py:301-305 rearranges '(b t) c h w' so every frame has its own) ----
-__global__ void gn_partial_kernel(const bf16* __restrict__ x, double* __restrict__ sums, int64_t HW, int C, int G,
+__global__ void gn_partial_kernel(const bf16* __restrict__ x, double* __restrict__ part, int64_t HW, int C, int G,
                                   int pix_per_block) {
-  extern __shared__ float sm[];  // [2*C]
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
+  // Deterministic (no atomics: a decode must be reproducible bit for bit, tests/test_vae_gpu.py): every thread sums a
+  // fixed pixel subset of one 8-channel vector, the block reduces in a fixed order, one (sum, sum of squares) pair per
+  // (frame, block, group) goes to the workspace and gn_finalize_kernel adds the blocks in order.
+  extern __shared__ float red[];  // [2][pstride][C]
   const int t = blockIdx.y;
   const int nvec = C >> 3;
   const int cv = threadIdx.x % nvec;
@@ -64,29 +65,40 @@ __global__ void gn_partial_kernel(const bf16* __restrict__ x, double* __restrict
       s[2 * k + 1] += f.y; q[2 * k + 1] += f.y * f.y;
     }
   }
+  float* rs = red + (size_t)prow * C + cv * 8;
+  float* rq = red + (size_t)(pstride + prow) * C + cv * 8;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    atomicAdd(&sm[cv * 8 + j], s[j]);
-    atomicAdd(&sm[C + cv * 8 + j], q[j]);
+    rs[j] = s[j];
+    rq[j] = q[j];
   }
   __syncthreads();
   const int cpg = C / G;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    float a = 0.f, b = 0.f;
-    for (int c = 0; c < cpg; ++c) {
-      a += sm[g * cpg + c];
-      b += sm[C + g * cpg + c];
-    }
-    atomicAdd(&sums[((int64_t)t * G + g) * 2], (double)a);
-    atomicAdd(&sums[((int64_t)t * G + g) * 2 + 1], (double)b);
+    double a = 0.0, b = 0.0;
+    for (int c = 0; c < cpg; ++c)
+      for (int pr = 0; pr < pstride; ++pr) {
+        a += (double)red[(size_t)pr * C + g * cpg + c];
+        b += (double)red[(size_t)(pstride + pr) * C + g * cpg + c];
+      }
+    double* dst = part + (((int64_t)t * gridDim.x + blockIdx.x) * G + g) * 2;
+    dst[0] = a;
+    dst[1] = b;
   }
 }
-__global__ void gn_finalize_kernel(const double* __restrict__ sums, float* __restrict__ stats, int n, double count,
-                                   float eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void gn_finalize_kernel(const double* __restrict__ part, float* __restrict__ stats, int n, int G, int blocks,
+                                   double count, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (frame, group)
   if (i >= n) return;
-  const double mean = sums[2 * i] / count;
-  double var = sums[2 * i + 1] / count - mean * mean;
+  const int t = i / G, g = i % G;
+  double a = 0.0, b = 0.0;
+  for (int bx = 0; bx < blocks; ++bx) {
+    const double* src = part + (((int64_t)t * blocks + bx) * G + g) * 2;
+    a += src[0];
+    b += src[1];
+  }
+  const double mean = a / count;
+  double var = b / count - mean * mean;
   var = var < 0 ? 0 : var;
   stats[2 * i] = (float)mean;
   stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
@@ -251,8 +263,13 @@ extern "C" int ea_vae_prepare_latents(const void* z, const void* w, const void* 
   return check_launch("vae_prepare_latents_kernel");
 }
 
-extern "C" size_t ea_groupnorm_workspace(int64_t frames, int64_t groups) {
-  return (size_t)frames * groups * 2 * sizeof(double);
+static int gn_blocks(int64_t HW) {
+  const int b = (int)((HW + 4095) / 4096);
+  return b < 1 ? 1 : b;
+}
+
+extern "C" size_t ea_groupnorm_workspace(int64_t frames, int64_t HW, int64_t groups) {
+  return (size_t)frames * gn_blocks(HW) * groups * 2 * sizeof(double);
 }
 
 extern "C" int ea_groupnorm_stats(const void* x, void* stats, void* workspace, size_t workspace_bytes, int64_t frames,
@@ -261,20 +278,19 @@ extern "C" int ea_groupnorm_stats(const void* x, void* stats, void* workspace, s
   EA_REQUIRE(x && stats && workspace, "ea_groupnorm_stats: null pointer");
   EA_REQUIRE(C % 8 == 0 && C % groups == 0 && C <= 2048 && 256 % (C / 8) == 0,
              "ea_groupnorm_stats: C must be a multiple of 8 dividing into 256 threads, and of groups");
-  if (workspace_bytes < ea_groupnorm_workspace(frames, groups))
+  if (workspace_bytes < ea_groupnorm_workspace(frames, HW, groups))
     return fail(EA_ERR_WORKSPACE, "ea_groupnorm_stats: workspace too small");
   EA_REQUIRE(frames <= 65535, "ea_groupnorm_stats: too many frames");
-  cudaMemsetAsync(workspace, 0, ea_groupnorm_workspace(frames, groups), stream);
-  int blocks_x = (int)((HW + 4095) / 4096);
-  if (blocks_x < 1) blocks_x = 1;
+  const int blocks_x = gn_blocks(HW);
   const int pix_per_block = (int)((HW + blocks_x - 1) / blocks_x);
   dim3 grid((unsigned)blocks_x, (unsigned)frames);
-  gn_partial_kernel<<<grid, 256, 2 * C * sizeof(float), stream>>>((const bf16*)x, (double*)workspace, HW, (int)C,
-                                                                  (int)groups, pix_per_block);
+  const size_t smem = 2 * (size_t)(256 / (C / 8)) * C * sizeof(float);  // 16 KB
+  gn_partial_kernel<<<grid, 256, smem, stream>>>((const bf16*)x, (double*)workspace, HW, (int)C, (int)groups,
+                                                 pix_per_block);
   count_launch();
   const int n = (int)(frames * groups);
-  gn_finalize_kernel<<<(n + 127) / 128, 128, 0, stream>>>((const double*)workspace, (float*)stats, n,
-                                                          (double)HW * (double)(C / groups), eps);
+  gn_finalize_kernel<<<(n + 127) / 128, 128, 0, stream>>>((const double*)workspace, (float*)stats, n, (int)groups,
+                                                          blocks_x, (double)HW * (double)(C / groups), eps);
   count_launch();
   return check_launch("groupnorm_stats");
 }

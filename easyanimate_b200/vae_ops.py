@@ -59,7 +59,7 @@ def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: 
     T, H, W, Cc = x.shape
     assert x.is_contiguous()
     stats = torch.empty((T, groups, 2), device=x.device, dtype=torch.float32)
-    ws_bytes = L.ea_groupnorm_workspace(T, groups)
+    ws_bytes = L.ea_groupnorm_workspace(T, H * W, groups)
     ws = torch.empty((ws_bytes,), device=x.device, dtype=torch.uint8)
     L.check(L.ea_groupnorm_stats(_p(x), _p(stats), _p(ws), ws_bytes, T, H * W, Cc, groups, eps, _stream()),
             "ea_groupnorm_stats")

@@ -235,7 +235,7 @@ int ea_vae_prepare_latents(const void* z, const void* w, const void* bias, void*
 
 /* Per-frame GroupNorm (common.py:301-319 with set_3dgroupnorm; omnigen_enc_dec.py:603-609):
  * stats[frames,groups,2] = (mean, rstd) fp32; workspace = ea_groupnorm_workspace() bytes of scratch. */
-size_t ea_groupnorm_workspace(int64_t frames, int64_t groups);
+size_t ea_groupnorm_workspace(int64_t frames, int64_t HW, int64_t groups);
 int ea_groupnorm_stats(const void* x, void* stats, void* workspace, size_t workspace_bytes, int64_t frames, int64_t HW,
                        int64_t C, int64_t groups, float eps, void* stream);
 /* y = [SiLU](bf16((x-mean)*rstd*gamma+beta)) */

@@ -57,6 +57,20 @@ def test_transformer_forward_matches_oracle(name, cfg, shape):
     three_way(got, ref, truth, name=name)
 
 
+def test_transformer_forward_is_deterministic():
+    """No atomics on the forward path: two runs agree bit for bit (what CFG-parallel == batch-of-2 relies on)."""
+    from oracle import dit
+    _, _, ours = _build(CFG_TINY)
+    lat, enc, t = _inputs(2, 16, 3, 8, 12, 40, CFG_TINY["text_embed_dim"])
+    rope = dit.rope_for_video(8 * 8, 12 * 8, 3)
+    args = (lat.to(bf16).cuda(), t.to(bf16).cuda())
+    kw = dict(encoder_hidden_states=enc.to(bf16).cuda(), image_rotary_emb=(rope[0].cuda(), rope[1].cuda()), return_dict=False)
+    with torch.no_grad():
+        a = ours(*args, **kw)[0]
+        b = ours(*args, **kw)[0]
+    assert torch.equal(a, b)
+
+
 def test_transformer_i2v_inpaint_channels():
     """predict_i2v path: inpaint_latents (1 mask + 16 masked-video channels) concatenated on channels -> in_channels 33."""
     from oracle import dit
