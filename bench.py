@@ -141,6 +141,42 @@ def cpu_oracle_rate(seconds_budget: float = 15.0, threads: int | None = None):
     return fl / per, desc, threads, per
 
 
+def vae_decode_line(preset, dev, reps=3):
+    """Secondary metric of the path: AutoencoderKLMagvit.decode of the workload's latent, untiled
+    whole-sequence decode on one GPU, output MPix/s (device-resident latents, CUDA events, after one warm-up)."""
+    import torch
+    from easyanimate_b200.autoencoder_magvit import AutoencoderKLMagvit
+    bf16 = torch.bfloat16
+    with torch.device(dev):
+        vae = AutoencoderKLMagvit(latent_channels=16, cache_mag_vae=True, spatial_group_norm=True,
+                                  mid_block_attention_type="spatial", mini_batch_decoder=1, scaling_factor=0.7125).to(bf16)
+    with torch.no_grad():
+        for n, p in vae.named_parameters():
+            if p.dim() >= 2:
+                p.normal_(0, (1.0 / p[0].numel()) ** 0.5)
+            elif "norm" in n and n.endswith("weight"):
+                p.normal_(1.0, 0.05)
+            else:
+                p.normal_(0, 0.05)
+    vae.use_tiling = False
+    z = torch.randn((1, 16, preset["F"], preset["h"], preset["w"]), device=dev).to(bf16)
+    out = vae.decode(z).sample
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        vae.decode(z)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = statistics.median(times)
+    mpix = out.shape[2] * out.shape[3] * out.shape[4] / 1e6
+    return {"value": mpix / ms * 1e3, "unit": "MPix/s", "ms": ms, "frames": int(out.shape[2]),
+            "resolution": [int(out.shape[3]), int(out.shape[4])], "mode": "untiled whole-sequence decode, random-init weights",
+            "finite": bool(torch.isfinite(out).all())}
+
+
 def run_reference_arm(args, preset):
     """--impl reference: the reference's own CPU implementation of the path on the host cores (oracle port)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -316,6 +352,8 @@ def main():
                          "launches_timed": len(attn_ms), "avg_ms": attn_avg_ms, "flops_per_launch": attn_flops,
                          "share_of_step": (sum(attn_ms) / ms_total) if attn_ms else None},
         }
+        if world == 1 and not args.no_vae:
+            line["vae_decode"] = vae_decode_line(preset, dev)
         if world == 1 and not args.no_cpu_baseline:
             rate, desc, cores, _ = cpu_oracle_rate(seconds_budget=12.0)
             line["cpu_baseline"] = {"value": rate / flops_step, "unit": "steps/s", "cores": cores, "kind": "port", "sample": desc}
