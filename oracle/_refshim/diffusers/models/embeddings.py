@@ -1,0 +1,73 @@
+"""diffusers.models.embeddings: sinusoidal timestep projection, the 2-layer timestep MLP and the real-valued rotary
+application (embeddings.py get_timestep_embedding / Timesteps / TimestepEmbedding / apply_rotary_emb, 0.30)."""
+import math
+
+import torch
+from torch import nn
+
+from ._placeholder import placeholder
+
+
+def get_timestep_embedding(timesteps, embedding_dim, flip_sin_to_cos=False, downscale_freq_shift=1, scale=1,
+                           max_period=10000):
+    assert len(timesteps.shape) == 1, "Timesteps should be a 1d-array"
+    half_dim = embedding_dim // 2
+    exponent = -math.log(max_period) * torch.arange(start=0, end=half_dim, dtype=torch.float32, device=timesteps.device)
+    exponent = exponent / (half_dim - downscale_freq_shift)
+    emb = torch.exp(exponent)
+    emb = timesteps[:, None].float() * emb[None, :]
+    emb = scale * emb
+    emb = torch.cat([torch.sin(emb), torch.cos(emb)], dim=-1)
+    if flip_sin_to_cos:
+        emb = torch.cat([emb[:, half_dim:], emb[:, :half_dim]], dim=-1)
+    if embedding_dim % 2 == 1:
+        emb = torch.nn.functional.pad(emb, (0, 1, 0, 0))
+    return emb
+
+
+class Timesteps(nn.Module):
+    def __init__(self, num_channels, flip_sin_to_cos, downscale_freq_shift, scale=1):
+        super().__init__()
+        self.num_channels, self.flip_sin_to_cos = num_channels, flip_sin_to_cos
+        self.downscale_freq_shift, self.scale = downscale_freq_shift, scale
+
+    def forward(self, timesteps):
+        return get_timestep_embedding(timesteps, self.num_channels, flip_sin_to_cos=self.flip_sin_to_cos,
+                                      downscale_freq_shift=self.downscale_freq_shift, scale=self.scale)
+
+
+class TimestepEmbedding(nn.Module):
+    def __init__(self, in_channels, time_embed_dim, act_fn="silu", out_dim=None, post_act_fn=None, cond_proj_dim=None,
+                 sample_proj_bias=True):
+        super().__init__()
+        assert act_fn == "silu" and post_act_fn is None and cond_proj_dim is None
+        self.linear_1 = nn.Linear(in_channels, time_embed_dim, sample_proj_bias)
+        self.act = nn.SiLU()
+        self.linear_2 = nn.Linear(time_embed_dim, out_dim if out_dim is not None else time_embed_dim, sample_proj_bias)
+
+    def forward(self, sample, condition=None):
+        return self.linear_2(self.act(self.linear_1(sample)))
+
+
+def apply_rotary_emb(x, freqs_cis, use_real=True, use_real_unbind_dim=-1):
+    assert use_real and use_real_unbind_dim == -1
+    cos, sin = freqs_cis  # [S, D]
+    cos, sin = cos[None, None].to(x.device), sin[None, None].to(x.device)
+    x_real, x_imag = x.reshape(*x.shape[:-1], -1, 2).unbind(-1)  # [B, H, S, D//2]
+    x_rotated = torch.stack([-x_imag, x_real], dim=-1).flatten(3)
+    return (x.float() * cos + x_rotated.float() * sin).to(x.dtype)
+
+
+PatchEmbed = placeholder("PatchEmbed")
+PixArtAlphaTextProjection = placeholder("PixArtAlphaTextProjection")
+SinusoidalPositionalEmbedding = placeholder("SinusoidalPositionalEmbedding")
+CombinedTimestepLabelEmbeddings = placeholder("CombinedTimestepLabelEmbeddings")
+PixArtAlphaCombinedTimestepSizeEmbeddings = placeholder("PixArtAlphaCombinedTimestepSizeEmbeddings")
+
+
+def get_2d_sincos_pos_embed(*a, **k):
+    raise NotImplementedError("diffusers shim: get_2d_sincos_pos_embed is not on the EasyAnimateV5.1 path")
+
+
+def get_3d_sincos_pos_embed(*a, **k):
+    raise NotImplementedError("diffusers shim: get_3d_sincos_pos_embed is not on the EasyAnimateV5.1 path")

@@ -1,0 +1,11 @@
+from dataclasses import dataclass
+
+import torch
+
+
+@dataclass
+class Transformer2DModelOutput:
+    sample: "torch.Tensor"
+
+    def __getitem__(self, i):
+        return (self.sample,)[i]

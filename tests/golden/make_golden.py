@@ -5,8 +5,12 @@ oracle/ref_vae.py and run in its v5.1 execution mode (cache_mag_vae=True, one la
 padding_flag 3/4) in fp32 on CPU.  Weights come from oracle.vae.init_weights_(seed) so the fixtures stay small:
 only inputs and outputs are stored.
 
-DiT: the reference transformer cannot be imported here (diffusers missing), so DiT fixtures are produced by the
-oracle restatement and are marked `source=oracle` (parity unpinned, see oracle/dit.py).
+DiT: the reference's own `EasyAnimateTransformer3DModel` (easyanimate/models/transformer3d.py with attention.py,
+processor.py, norm.py, executed unmodified) is imported through oracle/ref_dit.py - diffusers itself is not installable
+here, so the third-party primitives it uses come from oracle/_refshim (restated from diffusers 0.30/0.31) - and run in
+fp32 on CPU: `dit_ref_*.safetensors` hold inputs and the reference's outputs (T2V forward, I2V forward with
+inpaint_latents, a 6-call TeaCache sequence with its skip decisions).  `dit_tiny` (3-step CFG denoise loop, scheduler
+and RoPE tables) is produced by the oracle and is a regression fixture, not a reference vector.
 
 Usage:  python tests/golden/make_golden.py
 """
@@ -20,7 +24,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-from oracle import dit, ref_vae, vae  # noqa: E402
+from oracle import dit, ref_dit, ref_vae, vae  # noqa: E402
 
 VAE_CASES = {
     # name: (block_out_channels, mid_attention, z shape, seed)
@@ -65,8 +69,70 @@ def make_dit():
     print("dit_tiny", tuple(out.shape), float(out.std()))
 
 
+DIT_REF_CASES = {
+    # name: (config overrides, (B, F, H, W, S_text), weight seed, inpaint channels)
+    "dit_ref_t2v": (dict(), (2, 3, 8, 12, 40), 21, 0),
+    "dit_ref_i2v_inpaint": (dict(in_channels=33), (1, 2, 6, 10, 7), 22, 17),
+    "dit_ref_3heads_3layers": (dict(num_attention_heads=3, num_layers=3, time_embed_dim=96, text_embed_dim=192), (1, 1, 4, 6, 9), 23, 0),
+}
+
+
+def _dit_inputs(cfg, shape, seed, inpaint_c):
+    B, F, H, W, St = shape
+    g = torch.Generator().manual_seed(seed + 100)
+    t = {"latents": torch.randn(B, 16, F, H, W, generator=g), "encoder_hidden_states": torch.randn(B, St, cfg["text_embed_dim"], generator=g) * 3.0,
+         "timestep": torch.tensor([937.0, 421.0][:B])}
+    if inpaint_c:
+        t["inpaint_latents"] = torch.randn(B, inpaint_c, F, H, W, generator=g)
+    return t
+
+
+def make_dit_reference():
+    """Golden vectors from the REFERENCE's transformer code (oracle/ref_dit.py)."""
+    for name, (over, shape, seed, inpaint_c) in DIT_REF_CASES.items():
+        cfg = {**DIT_CFG, **over}
+        ref = ref_dit.reference_transformer(**cfg).eval()
+        ref.load_state_dict(dit.init_weights_(dit.OracleTransformer3D(**cfg), seed).state_dict(), strict=True)
+        t = _dit_inputs(cfg, shape, seed, inpaint_c)
+        rope = dit.rope_for_video(shape[2] * 8, shape[3] * 8, shape[1])
+        with torch.no_grad():
+            out = ref(t["latents"], t["timestep"], encoder_hidden_states=t["encoder_hidden_states"], image_rotary_emb=rope,
+                      inpaint_latents=t.get("inpaint_latents"), return_dict=False)[0]
+        t["out"] = out.contiguous()
+        save_file(t, os.path.join(HERE, f"{name}.safetensors"),
+                  metadata={"source": "reference EasyAnimateTransformer3DModel (fp32, CPU, diffusers primitives from oracle/_refshim)",
+                            "seed": str(seed), "config": repr(cfg), "shape": repr(shape)})
+        print(name, tuple(out.shape), float(out.std()))
+    # TeaCache: 6 calls with slowly drifting inputs; record every output and which calls were skipped
+    cfg, seed = DIT_CFG, 24
+    ref = ref_dit.reference_transformer(**cfg).eval()
+    ref.load_state_dict(dit.init_weights_(dit.OracleTransformer3D(**cfg), seed).state_dict(), strict=True)
+    ref.enable_teacache(6, 0.08, coefficients=TEACACHE_COEFFS)
+    base = _dit_inputs(cfg, (2, 3, 8, 12, 40), seed, 0)
+    rope = dit.rope_for_video(64, 96, 3)
+    outs, skipped = [], []
+    with torch.no_grad():
+        for i in range(6):
+            lat = base["latents"] * (1.0 - 0.01 * i)
+            tt = base["timestep"] - 30.0 * i
+            before = ref.teacache.previous_residual
+            out = ref(lat, tt, encoder_hidden_states=base["encoder_hidden_states"], image_rotary_emb=rope, return_dict=False)[0]
+            skipped.append(1.0 if (ref.teacache.previous_residual is before and i > 0) else 0.0)
+            outs.append(out)
+    base["outs"] = torch.stack(outs).contiguous()
+    base["skipped"] = torch.tensor(skipped)
+    save_file(base, os.path.join(HERE, "dit_ref_teacache.safetensors"),
+              metadata={"source": "reference EasyAnimateTransformer3DModel + TeaCache (fp32, CPU)", "seed": str(seed),
+                        "config": repr(cfg), "num_steps": "6", "rel_l1_thresh": "0.08", "coefficients": repr(TEACACHE_COEFFS)})
+    print("dit_ref_teacache skipped:", skipped)
+
+
+TEACACHE_COEFFS = [1.07862322, -4.19362456, 3.06725828, 0.33161686, 0.02374758]  # transformer3d.py:131 (v5.1-7b)
+
+
 if __name__ == "__main__":
     if not ref_vae.available():
         raise SystemExit("/root/reference not present: golden VAE vectors can only be minted in the authoring container")
     make_vae()
     make_dit()
+    make_dit_reference()

@@ -57,6 +57,39 @@ def test_transformer_forward_matches_oracle(name, cfg, shape):
     three_way(got, ref, truth, name=name)
 
 
+@pytest.mark.parametrize("name", ["dit_ref_t2v", "dit_ref_i2v_inpaint", "dit_ref_3heads_3layers"])
+def test_transformer_forward_matches_reference_golden(name):
+    """Against outputs of the REFERENCE's own EasyAnimateTransformer3DModel (fp32, minted by tests/golden/make_golden.py
+    in the authoring container): our bf16 kernels are as close to it as the bf16 oracle is."""
+    import ast
+    import os
+    from safetensors import safe_open
+    from safetensors.torch import load_file
+    from oracle import dit
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"{name}.safetensors")
+    t = load_file(path)
+    with safe_open(path, framework="pt") as f:
+        meta = f.metadata()
+    cfg = ast.literal_eval(meta["config"])
+    B, F, H, W, St = ast.literal_eval(meta["shape"])
+    o32, ob, ours = _build(cfg, seed=int(meta["seed"]))
+    rope = dit.rope_for_video(H * 8, W * 8, F)
+    inp = t.get("inpaint_latents")
+    with torch.no_grad():
+        tb = t["timestep"].to(bf16)
+        truth32 = o32(t["latents"].to(bf16).float(), tb.float(), encoder_hidden_states=t["encoder_hidden_states"].to(bf16).float(),
+                      image_rotary_emb=rope, inpaint_latents=None if inp is None else inp.to(bf16).float())[0]
+        ref = ob(t["latents"].to(bf16), tb, encoder_hidden_states=t["encoder_hidden_states"].to(bf16), image_rotary_emb=rope,
+                 inpaint_latents=None if inp is None else inp.to(bf16))[0]
+        got = ours(t["latents"].to(bf16).cuda(), tb.cuda(), encoder_hidden_states=t["encoder_hidden_states"].to(bf16).cuda(),
+                   image_rotary_emb=(rope[0].cuda(), rope[1].cuda()), inpaint_latents=None if inp is None else inp.to(bf16).cuda(),
+                   return_dict=False)[0]
+    # the fixture is the reference on UNROUNDED fp32 weights and inputs; the bf16 rounding of weights/inputs is common to
+    # `ref` and `got`, so both are compared against the fixture itself
+    three_way(got, ref, t["out"], name=name + "_vs_reference_fixture")
+    three_way(got, ref, truth32, name=name)
+
+
 def test_transformer_forward_is_deterministic():
     """No atomics on the forward path: two runs agree bit for bit (what CFG-parallel == batch-of-2 relies on)."""
     from oracle import dit

@@ -8,7 +8,7 @@ import torch
 from safetensors import safe_open
 from safetensors.torch import load_file
 
-from oracle import dit, ref_vae, vae
+from oracle import dit, ref_dit, ref_vae, vae
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -53,6 +53,65 @@ def test_vae_tiled_decode_oracle_shapes_and_seams():
         full = m.decode(z)[0]
     assert tiled.shape == full.shape == (1, 3, 5, 96, 160)
     assert torch.isfinite(tiled).all()
+
+
+def _dit_case(name):
+    path = os.path.join(GOLD, f"{name}.safetensors")
+    t, meta = load_file(path), _meta(path)
+    cfg = ast.literal_eval(meta["config"])
+    m = dit.init_weights_(dit.OracleTransformer3D(**cfg), int(meta["seed"])).eval()
+    return t, meta, cfg, m
+
+
+@pytest.mark.parametrize("name", ["dit_ref_t2v", "dit_ref_i2v_inpaint", "dit_ref_3heads_3layers"])
+def test_dit_oracle_matches_reference_golden(name):
+    """Outputs of the REFERENCE's EasyAnimateTransformer3DModel (tests/golden/make_golden.py::make_dit_reference)."""
+    t, meta, cfg, m = _dit_case(name)
+    B, F, H, W, St = ast.literal_eval(meta["shape"])
+    rope = dit.rope_for_video(H * 8, W * 8, F)
+    with torch.no_grad():
+        out = m(t["latents"], t["timestep"], encoder_hidden_states=t["encoder_hidden_states"], image_rotary_emb=rope,
+                inpaint_latents=t.get("inpaint_latents"))[0]
+    torch.testing.assert_close(out, t["out"], rtol=1e-5, atol=1e-6)
+
+
+def test_dit_oracle_teacache_matches_reference_golden():
+    """Six calls of the reference model with TeaCache enabled: same skip decisions, same outputs."""
+    t, meta, cfg, m = _dit_case("dit_ref_teacache")
+    m.teacache = dit.OracleTeaCache(ast.literal_eval(meta["coefficients"]), int(meta["num_steps"]), float(meta["rel_l1_thresh"]))
+    rope = dit.rope_for_video(64, 96, 3)
+    skipped = []
+    with torch.no_grad():
+        for i in range(6):
+            before = m.teacache.skipped
+            out = m(t["latents"] * (1.0 - 0.01 * i), t["timestep"] - 30.0 * i, encoder_hidden_states=t["encoder_hidden_states"],
+                    image_rotary_emb=rope)[0]
+            skipped.append(float(m.teacache.skipped - before))
+            torch.testing.assert_close(out, t["outs"][i], rtol=1e-5, atol=1e-6)
+    assert skipped == t["skipped"].tolist() and sum(skipped) == 3
+
+
+@pytest.mark.skipif(not ref_dit.available(), reason="/root/reference only exists in the authoring container")
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_dit_oracle_matches_live_reference_bit_for_bit(dtype):
+    """The reference's own transformer3d.py / attention.py / processor.py / norm.py, executed unmodified
+    (oracle/ref_dit.py), against the restatement with the same weights: identical in fp32 and in bf16 (the op-by-op
+    rounding points are the same)."""
+    cfg = dict(num_attention_heads=2, attention_head_dim=64, in_channels=16, out_channels=16, patch_size=2, num_layers=2,
+               time_embed_dim=64, add_norm_text_encoder=True, text_embed_dim=128, text_embed_dim_t5=None)
+    mine = dit.init_weights_(dit.OracleTransformer3D(**cfg), 7).eval()
+    ref = ref_dit.reference_transformer(**cfg).eval()
+    ref.load_state_dict(mine.state_dict(), strict=True)
+    mine, ref = mine.to(dtype), ref.to(dtype)
+    g = torch.Generator().manual_seed(1)
+    lat = torch.randn(2, 16, 3, 8, 12, generator=g).to(dtype)
+    enc = (torch.randn(2, 40, 128, generator=g) * 3).to(dtype)
+    tt = torch.tensor([937.0, 421.0]).to(dtype)
+    rope = dit.rope_for_video(64, 96, 3)
+    with torch.no_grad():
+        a = ref(lat, tt, encoder_hidden_states=enc, image_rotary_emb=rope, return_dict=False)[0]
+        b = mine(lat, tt, encoder_hidden_states=enc, image_rotary_emb=rope)[0]
+    assert torch.equal(a, b)
 
 
 def test_dit_golden_regression():
