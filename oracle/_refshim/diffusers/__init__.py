@@ -7,3 +7,8 @@ What the EasyAnimateV5.1 path actually executes from diffusers is restated here 
 (Attention container, FeedForward/GELU, AdaLayerNorm, Timesteps/TimestepEmbedding, apply_rotary_emb, ConfigMixin /
 ModelMixin plumbing); every other imported name is a placeholder that raises if it is ever instantiated."""
 __version__ = "0.31.0"
+
+
+class AutoencoderKL:  # imported by easyanimate/models/autoencoder_magvit.py:41, never used on the decode path
+    def __init__(self, *a, **k):
+        raise NotImplementedError("diffusers shim: AutoencoderKL is a placeholder")

@@ -46,3 +46,7 @@ class Attention(nn.Module):
 AttentionProcessor = placeholder("AttentionProcessor")
 AttnProcessor2_0 = placeholder("AttnProcessor2_0")
 HunyuanAttnProcessor2_0 = placeholder("HunyuanAttnProcessor2_0")
+AttnAddedKVProcessor = placeholder("AttnAddedKVProcessor")
+AttnProcessor = placeholder("AttnProcessor")
+ADDED_KV_ATTENTION_PROCESSORS = ()
+CROSS_ATTENTION_PROCESSORS = ()

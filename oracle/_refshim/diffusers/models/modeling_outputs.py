@@ -9,3 +9,11 @@ class Transformer2DModelOutput:
 
     def __getitem__(self, i):
         return (self.sample,)[i]
+
+
+@dataclass
+class AutoencoderKLOutput:
+    latent_dist: object
+
+    def __getitem__(self, i):
+        return (self.latent_dist,)[i]

@@ -69,6 +69,24 @@ def make_dit():
     print("dit_tiny", tuple(out.shape), float(out.std()))
 
 
+def make_vae_tiled():
+    """The reference's AutoencoderKLMagvit.tiled_decode (autoencoder_magvit.py:381-448) on a latent that needs 3 x 3
+    tiles plus the lower-right corner pass; also its untiled decode of the same latent."""
+    boc, seed = (64, 64, 128, 128), 31
+    ref = ref_vae.reference_autoencoder(block_out_channels=boc, use_tiling=True, tile_sample_min_size=64)
+    mine = vae.init_weights_(vae.OracleAutoencoderKLMagvit(block_out_channels=boc, use_tiling=True, tile_sample_min_size=64), seed)
+    ref.load_state_dict(mine.state_dict(), strict=False)
+    z = torch.randn(1, 16, 2, 14, 13, generator=torch.Generator().manual_seed(seed + 100))
+    with torch.no_grad():
+        tiled = ref.decode(z).sample
+        ref.use_tiling = False
+        full = ref.decode(z).sample
+    save_file({"z": z, "out_tiled": tiled.contiguous(), "out_untiled": full.contiguous()}, os.path.join(HERE, "vae_ref_tiled.safetensors"),
+              metadata={"source": "reference AutoencoderKLMagvit.decode (tiled_decode and untiled, fp32, CPU)", "seed": str(seed),
+                        "block_out_channels": str(boc), "tile_sample_min_size": "64"})
+    print("vae_ref_tiled", tuple(tiled.shape), float((tiled - full).abs().max()))
+
+
 DIT_REF_CASES = {
     # name: (config overrides, (B, F, H, W, S_text), weight seed, inpaint channels)
     "dit_ref_t2v": (dict(), (2, 3, 8, 12, 40), 21, 0),
@@ -134,5 +152,6 @@ if __name__ == "__main__":
     if not ref_vae.available():
         raise SystemExit("/root/reference not present: golden VAE vectors can only be minted in the authoring container")
     make_vae()
+    make_vae_tiled()
     make_dit()
     make_dit_reference()

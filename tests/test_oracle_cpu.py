@@ -43,6 +43,34 @@ def test_vae_oracle_matches_live_reference(cache):
         torch.testing.assert_close(mine(z), ref(z), rtol=1e-4, atol=1e-4)
 
 
+def test_vae_oracle_wrapper_matches_reference_golden():
+    """decode / tiled_decode of the REFERENCE's AutoencoderKLMagvit wrapper (post_quant_conv, 3 x 3 tiles + the
+    lower-right corner pass, blend_v / blend_h order): tests/golden/make_golden.py::make_vae_tiled."""
+    path = os.path.join(GOLD, "vae_ref_tiled.safetensors")
+    t, meta = load_file(path), _meta(path)
+    boc = ast.literal_eval(meta["block_out_channels"])
+    m = vae.init_weights_(vae.OracleAutoencoderKLMagvit(block_out_channels=boc, use_tiling=True,
+                                                        tile_sample_min_size=int(meta["tile_sample_min_size"])), int(meta["seed"]))
+    with torch.no_grad():
+        tiled = m.decode(t["z"])[0]
+        m.use_tiling = False
+        full = m.decode(t["z"])[0]
+    torch.testing.assert_close(tiled, t["out_tiled"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(full, t["out_untiled"], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.skipif(not ref_vae.available(), reason="/root/reference only exists in the authoring container")
+def test_vae_oracle_wrapper_matches_live_reference():
+    boc = (64, 64, 128, 128)
+    ref = ref_vae.reference_autoencoder(block_out_channels=boc, use_tiling=True, tile_sample_min_size=64)
+    mine = vae.init_weights_(vae.OracleAutoencoderKLMagvit(block_out_channels=boc, use_tiling=True, tile_sample_min_size=64), 9)
+    missing, unexpected = ref.load_state_dict(mine.state_dict(), strict=False)
+    assert not unexpected and all(k.startswith(("encoder.", "quant_conv.")) for k in missing)
+    z = torch.randn(1, 16, 2, 12, 20, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        torch.testing.assert_close(mine.decode(z)[0], ref.decode(z).sample, rtol=1e-4, atol=1e-4)
+
+
 def test_vae_tiled_decode_oracle_shapes_and_seams():
     m = vae.init_weights_(vae.OracleAutoencoderKLMagvit(block_out_channels=(64, 64, 128, 128), use_tiling=True,
                                                         tile_sample_min_size=64, mid_block_use_attention=False), 9)

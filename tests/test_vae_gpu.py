@@ -166,3 +166,32 @@ def test_vae_tiled_decode_matches_oracle():
     # no atomics anywhere in the decode: a second run must reproduce the first bit for bit (the tile-parallel path,
     # tools/test_multigpu.py, compares ranks' tiles against a single-GPU decode with torch.equal)
     assert torch.equal(got, again)
+
+
+def test_vae_tiled_decode_matches_reference_golden():
+    """Against the output of the REFERENCE's own AutoencoderKLMagvit.tiled_decode (fp32; tests/golden/make_golden.py::
+    make_vae_tiled): 3 x 3 ragged tiles + the lower-right corner pass."""
+    import ast
+    import os
+    from safetensors import safe_open
+    from safetensors.torch import load_file
+    from oracle import vae
+    from easyanimate_b200.autoencoder_magvit import AutoencoderKLMagvit
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vae_ref_tiled.safetensors")
+    t = load_file(path)
+    with safe_open(path, framework="pt") as f:
+        meta = f.metadata()
+    boc = list(ast.literal_eval(meta["block_out_channels"]))
+    kw = dict(block_out_channels=boc, use_tiling=True, tile_sample_min_size=int(meta["tile_sample_min_size"]))
+    o32 = vae.init_weights_(vae.OracleAutoencoderKLMagvit(**kw), int(meta["seed"]))
+    ob = vae.OracleAutoencoderKLMagvit(**kw).to(bf16)
+    ob.load_state_dict({k: v.to(bf16) for k, v in o32.state_dict().items()})
+    ours = AutoencoderKLMagvit(latent_channels=16, cache_mag_vae=True, spatial_group_norm=True, mid_block_attention_type="spatial",
+                               **kw).to(bf16)
+    ours.load_state_dict(ob.state_dict(), strict=False)
+    ours = ours.cuda()
+    with torch.no_grad():
+        ref = ob.decode(t["z"].to(bf16))[0]
+        got = ours.decode(t["z"].to(bf16).cuda(), return_dict=False)[0]
+    assert got.shape == t["out_tiled"].shape
+    three_way(got, ref, t["out_tiled"], name="vae_tiled_vs_reference_fixture")
