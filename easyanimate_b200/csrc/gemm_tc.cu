@@ -8,7 +8,16 @@
 //   warps 4-7          : epilogue — tcgen05.ld (one accumulator row per thread), fused bias / GELU / gate+residual /
 //                        per-head LayerNorm + RoPE, bf16 stores.
 //
+// Large problems (at least four waves of 128x256 tiles) run as CTA PAIRS (gemm2_tc_kernel, tcgen05 cta_group::2): the
+// two CTAs of a cluster own the upper and lower 128 rows of a 256x256 tile, each loads its 128 rows of A and HALF of
+// the W tile, and the leader's single MMA thread issues M=256 instructions that read both halves of W from both SMs.
+// A 128x256 tile per SM pulls 48 KB through the SM's L2 port per 4.2 MFLOP; at the ~55 B/clk/SM that port sustains
+// (14-15 TB/s over 148 SMs, profiles/r01_ncu_conv3d_v1_summary.txt) that is ~1.3 PFLOP/s - what the one-CTA kernel
+// measured.  A plain cluster with TMA multicast of W did not help (the bytes still enter each SM); the pair takes 32 KB.
+//
 // Replaces the cuBLAS calls behind every nn.Linear of the reference path (see include/ea_b200.h for call sites).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "host.h"
 #include "../../include/ea_b200.h"
@@ -406,6 +415,193 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair variant: 256x256 tile per cluster of two, BN = 256 per CTA accumulator (128 rows x 256 fp32 columns, two
+// stages), 6 shared-memory stages of (A 128x64 + W-half 128x64).  Barrier protocol:
+//   full[s]   (leader's, count 2) : both producers arrive.expect_tx on it and both CTAs' TMA bytes complete on it
+//   empty[s]  (each CTA's own)    : the leader's tcgen05.commit multicasts the release to both CTAs
+//   tfull[a]  (each CTA's own)    : multicast commit after the last k-block of a tile
+//   tempty[a] (leader's, count 256): the epilogue threads of BOTH CTAs arrive (the peer's remotely)
+// ------------------------------------------------------------------------------------------------
+struct Gemm2Cfg {
+  static constexpr int kStages = 6;
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = 128 * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                const GemmDevArgs p) {
+  using Cfg = Gemm2Cfg;
+  constexpr int BN = 256;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tfull_bar = bars + 2 * kStages;
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int crank = (int)cluster_ctarank();
+  const int num_n_tiles = (p.N + BN - 1) / BN;
+  const int num_tiles = ((p.M + 2 * kBM - 1) / (2 * kBM)) * num_n_tiles;  // 256-row tiles
+  const int num_k_blocks = (p.K + kBK - 1) / kBK;
+  const int first_tile = (int)(blockIdx.x >> 1), tile_step = (int)(gridDim.x >> 1);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 2);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 256);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();  // both CTAs' barriers exist before anything arrives on them remotely
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs): own 128 rows of A, own half of the W tile; completion on the LEADER's barrier =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        const int m0 = (tile / num_n_tiles) * (2 * kBM) + crank * kBM;
+        const int n0 = (tile % num_n_tiles) * BN + crank * 128;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const uint32_t lfull = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          mbar_arrive_expect_tx_cluster(lfull, Cfg::kStageBytes);
+          tma_load_2d_2sm(smem_a + stage * Cfg::kABytes, &tmap_a, lfull, kb * kBK, m0);
+          tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &tmap_b, lfull, kb * kBK, n0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && crank == 0) {
+      // ===== MMA issuer (leader CTA only) =====
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait_cluster(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait_cluster(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) umma_ss_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_2sm(&empty_bar[stage], 0x3);
+          if (kb == num_k_blocks - 1) umma_commit_2sm(&tfull_bar[as], 0x3);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (both CTAs, own 128 rows) =====
+    const int ew = warp - 4;
+    int it = 0;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int m0 = (tile / num_n_tiles) * (2 * kBM) + crank * kBM;
+      const int n0 = (tile % num_n_tiles) * BN;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const int row = m0 + ew * 32 + lane;
+      const uint32_t trow = tmem_base + (uint32_t(ew * 32) << 16) + as * BN;
+      if constexpr (EPI == EPI_QKV) {
+#pragma unroll 1
+        for (int h = 0; h < BN / 64; ++h) {
+          if (n0 + h * 64 < p.N) epilogue_qkv_head(p, row, n0 + h * 64, trow + h * 64);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t acc[32];
+          __syncwarp();
+          tmem_ld32(trow + c * 32, acc);
+          tmem_ld_wait();
+          if (row < p.M && n0 + c * 32 < p.N) epilogue_chunk32<EPI>(p, row, n0 + c * 32, acc);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();  // no CTA leaves (or frees TMEM) while its peer may still signal it or read its shared memory
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int EPI>
+static int launch_gemm2(const void* a, int64_t lda, const void* w, int64_t ldw, const GemmDevArgs& p, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg;
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.M};
+    uint64_t strides[1] = {(uint64_t)lda * 2};
+    uint32_t box[2] = {kBK, kBM};
+    int rc = make_tmap_bf16(&ta, a, 2, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
+    uint64_t strides[1] = {(uint64_t)ldw * 2};
+    uint32_t box[2] = {kBK, 128};
+    int rc = make_tmap_bf16(&tb, w, 2, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  auto kern = gemm2_tc_kernel<EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return fail(EA_ERR_CUDA, std::string("cudaFuncSetAttribute(gemm2): ") + cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int num_tiles = ((p.M + 2 * kBM - 1) / (2 * kBM)) * ((p.N + 255) / 256);
+  const int clusters = num_tiles < sm_count() / 2 ? num_tiles : sm_count() / 2;
+  kern<<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  count_launch();
+  return check_launch("gemm2_tc_kernel");
+}
+
+// CTA pairs once there are at least four waves of 128x256 tiles (EA_GEMM_2SM=0 disables them: A/B measurements)
+static bool use_pairs(const GemmDevArgs& p) {
+  static const bool enabled = [] { const char* e = getenv("EA_GEMM_2SM"); return !(e && e[0] == '0'); }();
+  return enabled && p.N >= 256 && (int64_t)((p.M + kBM - 1) / kBM) * ((p.N + 255) / 256) >= 4 * sm_count();
+}
+
+// ------------------------------------------------------------------------------------------------
 // host launch
 // ------------------------------------------------------------------------------------------------
 template <int BN, int EPI>
@@ -448,6 +644,7 @@ static int dispatch_bn(const void* a, int64_t lda, const void* w, int64_t ldw, c
   const int sms = sm_count();
   auto tiles = [&](int bn) { return (int64_t)((p.M + kBM - 1) / kBM) * ((p.N + bn - 1) / bn); };
   // (ragged N is fine for every width: TMA zero-fills the missing weight rows, the epilogue masks the columns)
+  if (use_pairs(p)) return launch_gemm2<EPI>(a, lda, w, ldw, p, stream);
   if (p.N >= 256 && tiles(256) >= sms) return launch_gemm<256, EPI>(a, lda, w, ldw, p, stream);
   if (p.N >= 128 && tiles(128) >= sms / 2) return launch_gemm<128, EPI>(a, lda, w, ldw, p, stream);
   return launch_gemm<64, EPI>(a, lda, w, ldw, p, stream);
@@ -512,6 +709,7 @@ extern "C" int ea_qkv_gemm_ln_rope(const ea_qkv_args* g, void* stream_) {
   p.d = (int)g->d; p.heads = (int)(g->d / 64); p.S = (int)g->S; p.seq_offset = (int)g->seq_offset;
   p.rows_per_batch = (int)g->rows_per_batch; p.ln_eps = g->ln_eps;
   // an N tile must not straddle the q|k|v boundaries: the widest tile that divides d
+  if (g->d % 256 == 0 && use_pairs(p)) return launch_gemm2<EPI_QKV>(g->a, g->lda, g->w, g->d, p, stream);
   if (g->d % 256 == 0) return launch_gemm<256, EPI_QKV>(g->a, g->lda, g->w, g->d, p, stream);
   if (g->d % 128 == 0) return launch_gemm<128, EPI_QKV>(g->a, g->lda, g->w, g->d, p, stream);
   return launch_gemm<64, EPI_QKV>(g->a, g->lda, g->w, g->d, p, stream);

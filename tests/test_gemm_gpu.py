@@ -19,6 +19,7 @@ def _ulp_close(out, ref, rtol=2 ** -7, atol=2e-2):
 @pytest.mark.parametrize("M,N,K", [
     (128, 256, 64), (128, 256, 512), (256, 512, 1024), (300, 256, 192), (1000, 3072, 3072),
     (128, 64, 64), (77, 64, 136), (512, 128, 3584), (4096, 12288, 3072), (2000, 3072, 12288), (37, 96, 72),
+    (4700, 4352, 320),  # cluster-of-two / multicast-W path with an odd number of row tiles (the last pair is half empty)
 ])
 def test_gemm_bias(M, N, K):
     from easyanimate_b200 import ops
