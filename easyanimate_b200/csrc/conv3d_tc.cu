@@ -14,6 +14,10 @@
 // Fused in the epilogue: bias, residual add, nearest temporal x2 duplication (frames >= 1), planar NCTHW store.
 // MT = number of 128-pixel sub-tiles one CTA accumulates against the same weight tile (2 => 256x BN CTA tile: the
 // kernel is L2->SM bandwidth bound at 128x128 (64 FLOP/B, ncu: 14.2 TB/s xbar), 256x128 moves 85 FLOP/B).
+// PAIR = CTA pairs (tcgen05 cta_group::2, see gemm_tc.cu): the two CTAs of a cluster take vertically adjacent pixel
+// tiles against the SAME weight tile, each loads half of it, the leader issues M=256 MMAs over both: 256 output
+// channels per pass for the wide layers (BN=256, MT=1: 32 KB per k-block and CTA instead of 48) and 40 KB instead of 48
+// for the 128-channel layers (BN=128, MT=2).
 #include "common.cuh"
 #include "host.h"
 #include "../../include/ea_b200.h"
@@ -39,10 +43,10 @@ struct ConvDevArgs {
   int T_out;
 };
 
-template <int BN, int MT>
+template <int BN, int MT, bool PAIR = false>
 struct ConvCfg {
   static constexpr int kABytes = MT * kCM * kCK * 2;
-  static constexpr int kBBytes = BN * kCK * 2;
+  static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * kCK * 2;  // PAIR: this CTA's half of the weight tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
   static constexpr int kAccCols = MT * BN;                       // one accumulator stage
@@ -51,11 +55,11 @@ struct ConvCfg {
   static_assert(kTmemCols <= 512, "accumulators exceed TMEM");
 };
 
-template <int BN, int MT>
+template <int BN, int MT, bool PAIR>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const ConvDevArgs p) {
-  using Cfg = ConvCfg<BN, MT>;
+  using Cfg = ConvCfg<BN, MT, PAIR>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -70,7 +74,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.T * p.tiles_h * p.tiles_w * p.tiles_n;
+  const int num_tiles = p.T * p.tiles_h * p.tiles_w * p.tiles_n;  // PAIR: p.tiles_h counts PAIRS of CTA tiles
+  const int crank = PAIR ? (int)cluster_ctarank() : 0;
+  const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int cchunks = p.Cin / kCK;
   const int num_k_blocks = p.kt_taps * 9 * cchunks;
 
@@ -78,18 +85,22 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], PAIR ? 2 : 1);  // PAIR: the leader's barrier takes both CTAs' producers and bytes
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], PAIR ? 256 : 128);  // PAIR: the leader's barrier takes both CTAs' epilogue threads
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+    else tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -98,7 +109,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     int r = tile / p.tiles_n;
     w0 = (r % p.tiles_w) * p.TW;
     r /= p.tiles_w;
-    h0 = (r % p.tiles_h) * (MT * p.TH);
+    h0 = ((r % p.tiles_h) * (PAIR ? 2 : 1) + crank) * (MT * p.TH);
     t = r / p.tiles_h;
   };
 
@@ -107,7 +118,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       // ===== TMA producer =====
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         int t, h0, w0, n0;
         decode_tile(tile, t, h0, w0, n0);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
@@ -117,39 +128,55 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           int tin = t + kt - (p.kt_taps - 1);  // causal: taps reach back in time; left edge replicates frame 0
           tin = tin < 0 ? 0 : tin;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_x, &full_bar[stage], c0, w0 + kw - 1, h0 + kh - 1, tin);
-          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_w, &full_bar[stage], tap * p.Cin + c0, n0);
+          if (PAIR) {
+            const uint32_t lfull = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            mbar_arrive_expect_tx_cluster(lfull, Cfg::kStageBytes);
+            tma_load_4d_2sm(smem_a + stage * Cfg::kABytes, &tmap_x, lfull, c0, w0 + kw - 1, h0 + kh - 1, tin);
+            tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &tmap_w, lfull, tap * p.Cin + c0, n0 + crank * (BN / 2));
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_x, &full_bar[stage], c0, w0 + kw - 1, h0 + kh - 1, tin);
+            tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_w, &full_bar[stage], tap * p.Cin + c0, n0);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc = umma_idesc_bf16(kCM, BN);
+    if (lane == 0 && crank == 0) {
+      // ===== MMA issuer (PAIR: the leader CTA issues for both) =====
+      constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * kCM : kCM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        if (PAIR) mbar_wait_cluster(&tempty_bar[as], aphase ^ 1);
+        else mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * Cfg::kAccCols;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          if (PAIR) mbar_wait_cluster(&full_bar[stage], phase);
+          else mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
 #pragma unroll
           for (int m = 0; m < MT; ++m) {
             const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes + m * (kCM * kCK * 2)));
 #pragma unroll
-            for (int k = 0; k < kCK / 16; ++k)
-              umma_ss(tmem_d + m * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < kCK / 16; ++k) {
+              if (PAIR) umma_ss_2sm(tmem_d + m * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              else umma_ss(tmem_d + m * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            }
           }
-          umma_commit(&empty_bar[stage]);
-          if (kb == num_k_blocks - 1) umma_commit(&tfull_bar[as]);
+          if (PAIR) {
+            umma_commit_2sm(&empty_bar[stage], 0x3);
+            if (kb == num_k_blocks - 1) umma_commit_2sm(&tfull_bar[as], 0x3);
+          } else {
+            umma_commit(&empty_bar[stage]);
+            if (kb == num_k_blocks - 1) umma_commit(&tfull_bar[as]);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -160,7 +187,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const int r = ew * 32 + lane;
     const int ph = r / p.TW, pw = r - ph * p.TW;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       int t, h0, w0, n0;
@@ -236,30 +263,33 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       }
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[as]);
+      if (PAIR) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
+      else mbar_arrive(&tempty_bar[as]);
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync();  // no CTA leaves while its peer may still signal it or read its shared memory
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (PAIR) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int BN, int MT>
+template <int BN, int MT, bool PAIR = false>
 static int launch_conv(const ea_conv3d_args* g, cudaStream_t stream) {
-  using Cfg = ConvCfg<BN, MT>;
+  using Cfg = ConvCfg<BN, MT, PAIR>;
   ConvDevArgs p{};
   p.T = (int)g->T; p.H = (int)g->H; p.W = (int)g->W; p.Cin = (int)g->Cin; p.Cout = (int)g->Cout;
   // tile shape: 8x16 or 4x32 pixels, whichever wastes fewer out-of-range pixels
   auto waste = [&](int th, int tw) {
-    th *= MT;
+    th *= MT * (PAIR ? 2 : 1);
     return (int64_t)((p.H + th - 1) / th) * th * ((p.W + tw - 1) / tw) * tw;
   };
   if (waste(4, 32) < waste(8, 16)) { p.TH = 4; p.TW = 32; } else { p.TH = 8; p.TW = 16; }
-  p.tiles_h = (p.H + MT * p.TH - 1) / (MT * p.TH);
+  p.tiles_h = (p.H + (PAIR ? 2 : 1) * MT * p.TH - 1) / ((PAIR ? 2 : 1) * MT * p.TH);  // PAIR: pairs of CTA tiles
   p.tiles_w = (p.W + p.TW - 1) / p.TW;
   p.tiles_n = (int)((g->Cout_pad + BN - 1) / BN);
   p.kt_taps = 3;
@@ -282,11 +312,11 @@ static int launch_conv(const ea_conv3d_args* g, cudaStream_t stream) {
     const uint64_t K = (uint64_t)27 * g->Cin;
     uint64_t dims[2] = {K, (uint64_t)g->Cout_pad};
     uint64_t strides[1] = {K * 2};
-    uint32_t box[2] = {kCK, (uint32_t)BN};
+    uint32_t box[2] = {kCK, (uint32_t)(PAIR ? BN / 2 : BN)};
     int rc = make_tmap_bf16(&tw, g->w, 2, dims, strides, box, true);
     if (rc) return rc;
   }
-  auto kern = conv3d_tc_kernel<BN, MT>;
+  auto kern = conv3d_tc_kernel<BN, MT, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -295,6 +325,25 @@ static int launch_conv(const ea_conv3d_args* g, cudaStream_t stream) {
   }
   const int64_t num_tiles = (int64_t)p.T * p.tiles_h * p.tiles_w * p.tiles_n;
   if (num_tiles >= (1ll << 31)) return fail(EA_ERR_INVALID, "ea_conv3d: too many tiles");
+  if (PAIR) {
+    const int clusters = (int)(num_tiles < sm_count() / 2 ? num_tiles : sm_count() / 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * clusters));
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tx, tw, p);
+    if (e != cudaSuccess) return fail(EA_ERR_CUDA, std::string("cudaLaunchKernelEx(conv, CTA pairs): ") + cudaGetErrorString(e));
+    count_launch();
+    return check_launch("conv3d_tc_kernel (CTA pairs)");
+  }
   const int grid = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
   kern<<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(tx, tw, p);
   count_launch();
@@ -319,6 +368,10 @@ extern "C" int ea_conv3d_causal(const ea_conv3d_args* g, void* stream_) {
   // frame is too small to fill the SMs with them.
   const int64_t tiles256 = g->T * ((g->H + 15) / 16) * ((g->W + 15) / 16) * ((g->Cout_pad + 127) / 128);
   const bool big = tiles256 >= 2 * sm_count() && !(g->variant & 1);
+  // CTA pairs (variant bit1 disables them: A/B measurements) once there are at least four waves of pair tiles
+  const bool pairs = big && !(g->variant & 2) && tiles256 >= 8 * sm_count();
+  if (pairs && g->Cout_pad % 256 == 0) return launch_conv<256, 1, true>(g, stream);
+  if (pairs && g->Cout_pad % 128 == 0) return launch_conv<128, 2, true>(g, stream);
   if (g->Cout_pad % 128 == 0) return big ? launch_conv<128, 2>(g, stream) : launch_conv<128, 1>(g, stream);
   if (g->Cout_pad % 64 == 0) return big ? launch_conv<64, 2>(g, stream) : launch_conv<64, 1>(g, stream);
   return big ? launch_conv<32, 2>(g, stream) : launch_conv<32, 1>(g, stream);

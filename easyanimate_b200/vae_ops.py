@@ -11,7 +11,7 @@ import torch
 from . import _lib as L
 from .ops import _p, _req, _stream, bf16, gemm
 
-CONV_VARIANT = int(os.environ.get("EA_CONV_VARIANT", "0"), 0)  # bit0: force 128-pixel CTA tiles (A/B measurements)
+CONV_VARIANT = int(os.environ.get("EA_CONV_VARIANT", "0"), 0)  # bit0: force 128-pixel CTA tiles, bit1: no CTA pairs (A/B)
 
 
 def conv3d_causal(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, cout: int, *,

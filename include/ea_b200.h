@@ -223,7 +223,7 @@ typedef struct {
   int64_t T, H, W, Cin, Cout, Cout_pad;
   int32_t dup_frames;
   int32_t out_planar;
-  int32_t variant;      /* 0 = default tiling; bit0: force 128-pixel CTA tiles (A/B measurements) */
+  int32_t variant;      /* 0 = default tiling; bit0: force 128-pixel CTA tiles, bit1: no CTA pairs (A/B measurements) */
 } ea_conv3d_args;
 
 int ea_conv3d_causal(const ea_conv3d_args* args, void* stream);

@@ -32,7 +32,10 @@ def _ref_causal_conv(x_cl, w, b):
 @pytest.mark.parametrize("T,H,W,Cin,Cout", [(1, 8, 16, 64, 64), (3, 10, 20, 64, 128), (2, 9, 7, 128, 256), (4, 16, 32, 256, 128),
                                             (2, 24, 40, 512, 512),
                                             # large enough for the 256-pixel CTA tiles (two sub-tiles per CTA), exact and ragged
-                                            (5, 128, 160, 64, 128), (5, 122, 150, 64, 128), (3, 90, 160, 128, 256)])
+                                            (5, 128, 160, 64, 128), (5, 122, 150, 64, 128), (3, 90, 160, 128, 256),
+                                            # large enough for CTA pairs (cta_group::2): 256-wide weight tile / 128-wide with
+                                            # two sub-tiles; odd number of tile rows so the last pair is half empty
+                                            (3, 208, 256, 128, 256), (3, 400, 250, 64, 128)])
 def test_conv3d_causal(T, H, W, Cin, Cout):
     from easyanimate_b200 import vae_ops
     x = _rand((T, H, W, Cin), 1.0, 1)
