@@ -327,6 +327,7 @@ def main():
         attn_avg_ms = statistics.mean(attn_ms) if attn_ms else None
         achieved = attn_flops / (attn_avg_ms * 1e-3) / 1e12 if attn_avg_ms else None
         flops_step = 2 * dit_flops_per_forward(**preset)
+        act_bytes = B_attn * S * preset["heads"] * 64 * 2  # one [B, S, d] bf16 activation
         line = {
             "metric": "denoising-steps/sec @49f·720p bf16 (CFG step = 2 MMDiT forwards)", "value": value, "unit": "steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -334,8 +335,11 @@ def main():
             "config": {"workload": args.preset, "model": f"MMDiT d={preset['heads'] * 64} heads={preset['heads']} layers={preset['layers']}",
                        "params": n_params, "latent": [1, 16, F, h, w], "video": f"{4 * (F - 1) + 1}f {h * 8}x{w * 8}",
                        "tokens": S, "text_tokens": S_TEXT, "guidance_scale": GUIDANCE, "scheduler": "flow-match Euler shift=1",
-                       "parallelism": "single GPU (CFG batch 2)" if world == 1 else f"{n_videos} video(s) x CFG-parallel pair (1 all_gather of 6 MB per step)",
-                       "l2": "inputs_exceed_L2 (activations are GBs)", "tflop_per_step": flops_step / 1e12},
+                       "parallelism": "single GPU (CFG batch 2)" if world == 1 else
+                       f"{n_videos} video(s) x CFG-parallel pair (1 all_gather of {latents.numel() * 2 / 1e6:.2f} MB per step)",
+                       "l2": ("inputs_exceed_L2" if act_bytes > 126e6 else "inputs_fit_L2 (not a timing configuration)") +
+                             f" (one activation tensor of a forward is {act_bytes / 1e6:.0f} MB, weights {n_params * 2 / 1e9:.1f} GB)",
+                       "tflop_per_step": flops_step / 1e12},
             "model_tflops": flops_step * value / 1e12,
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": lat_host.numel() * 2 + emb_host.numel() * 2,
                     "d2h_bytes_per_step": out_host.numel() * 2},
