@@ -1,4 +1,5 @@
-"""ORACLE (test infrastructure only) — CPU restatement of AutoencoderKLMagvit.decode for EasyAnimateV5.1.
+"""ORACLE (test infrastructure only) — CPU restatement of AutoencoderKLMagvit.decode (and, as preparation for the I2V
+conditioning row of SURVEY.md §8(f), .encode) for EasyAnimateV5.1.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may import
 this module; it is the checker, never the product path.
@@ -182,12 +183,85 @@ class OracleDecoder(nn.Module):
         return self.conv_out(x)
 
 
+class DownsampleConv3d(nn.Conv3d):
+    """The convolution of SpatialDownsampler3D / SpatialTemporalDownsampler3D (downsamplers.py:24-46,74-96): kernel 3,
+    stride (t_stride, 2, 2), no conv padding - the downsampler zero-pads one pixel on the right and bottom - and the causal
+    left replicate pad of CausalConv3d.  Whole-sequence form of the chunked padding_flag 3/4 path (common.py:97-141): output
+    frame k reads input frames (s k - 2, s k - 1, s k) with negative indices clamped to 0."""
+
+    def __init__(self, channels, t_stride):
+        super().__init__(channels, channels, kernel_size=3, stride=(t_stride, 2, 2), padding=0)
+
+    def forward(self, x):
+        x = F.pad(x, (0, 1, 0, 1))
+        x = F.pad(x, pad=(0, 0, 0, 0, 2, 0), mode="replicate")
+        return super().forward(x)
+
+
+class Downsampler(nn.Module):
+    def __init__(self, channels, temporal: bool):
+        super().__init__()
+        self.conv = DownsampleConv3d(channels, 2 if temporal else 1)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+class DownBlock(nn.Module):
+    """down_blocks.py:156-212 (SpatialDownBlock3D) / :272-328 (SpatialTemporalDownBlock3D), no gc_block."""
+
+    def __init__(self, in_channels, out_channels, num_layers, add_downsample, temporal):
+        super().__init__()
+        self.convs = nn.ModuleList([ResidualBlock3D(in_channels if i == 0 else out_channels, out_channels)
+                                    for i in range(num_layers)])
+        self.downsampler = Downsampler(out_channels, temporal) if add_downsample else None
+
+    def forward(self, x):
+        for conv in self.convs:
+            x = conv(x)
+        if self.downsampler is not None:
+            x = self.downsampler(x)
+        return x
+
+
+class OracleEncoder(nn.Module):
+    """omnigen_enc_dec.py:24-155 + single_forward :225-272 with spatial_group_norm=True, whole-sequence: the reference
+    encodes frame 0 alone and then mini_batch_encoder (4) frames at a time with the last two input frames of every
+    CausalConv3d cached (padding_flag 3/4), which is one causal pass over 1 + 4m frames."""
+
+    def __init__(self, in_channels=3, out_channels=16, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
+                 down_block_types=("SpatialDownBlock3D", "SpatialTemporalDownBlock3D", "SpatialTemporalDownBlock3D",
+                                   "SpatialTemporalDownBlock3D"), mid_block_use_attention=True, norm_num_groups=32,
+                 double_z=True):
+        super().__init__()
+        self.conv_in = CausalConv3d(in_channels, block_out_channels[0])
+        self.down_blocks = nn.ModuleList([])
+        out_ch = block_out_channels[0]
+        for i, typ in enumerate(down_block_types):
+            in_ch, out_ch = out_ch, block_out_channels[i]
+            final = i == len(block_out_channels) - 1
+            self.down_blocks.append(DownBlock(in_ch, out_ch, layers_per_block, add_downsample=not final,
+                                              temporal=typ == "SpatialTemporalDownBlock3D"))
+        self.mid_block = MidBlock3D(block_out_channels[-1], num_layers=layers_per_block, add_attention=mid_block_use_attention)
+        self.conv_norm_out = nn.GroupNorm(norm_num_groups, block_out_channels[-1], eps=1e-6)
+        self.conv_out = CausalConv3d(block_out_channels[-1], 2 * out_channels if double_z else out_channels)
+
+    def forward(self, x):
+        assert (x.shape[2] - 1) % 4 == 0, "the reference's chunking needs 1 + 4m frames"
+        x = self.conv_in(x)
+        for down in self.down_blocks:
+            x = down(x)
+        x = self.mid_block(x)
+        x = F.silu(frame_group_norm(self.conv_norm_out, x))
+        return self.conv_out(x)
+
+
 class OracleAutoencoderKLMagvit(nn.Module):
     """Decode side of autoencoder_magvit.py:59-505 (post_quant_conv + Decoder + tiling/blending)."""
 
     def __init__(self, latent_channels=16, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
                  mid_block_use_attention=True, use_tiling=False, use_tiling_decoder=False, tile_sample_min_size=384,
-                 tile_overlap_factor=0.25, scaling_factor=0.7125, **unused):
+                 tile_overlap_factor=0.25, scaling_factor=0.7125, with_encoder=False, in_channels=3, **unused):
         super().__init__()
         self.decoder = OracleDecoder(latent_channels, out_channels, block_out_channels, layers_per_block,
                                      mid_block_use_attention=mid_block_use_attention)
@@ -196,6 +270,10 @@ class OracleAutoencoderKLMagvit(nn.Module):
         self.tile_sample_min_size, self.tile_overlap_factor = tile_sample_min_size, tile_overlap_factor
         self.tile_latent_min_size = int(tile_sample_min_size / (2 ** (len(block_out_channels) - 1)))
         self.scaling_factor = scaling_factor
+        if with_encoder:  # registered AFTER the decode side so that init_weights_(seed) gives the decoder the same weights
+            self.encoder = OracleEncoder(in_channels, latent_channels, block_out_channels, layers_per_block,
+                                         mid_block_use_attention=mid_block_use_attention)
+            self.quant_conv = nn.Conv3d(2 * latent_channels, 2 * latent_channels, kernel_size=1)
 
     @staticmethod
     def blend_v(a, b, blend_extent):
@@ -242,6 +320,38 @@ class OracleAutoencoderKLMagvit(nn.Module):
         area = dec[:, :, :, -H:, -W:]
         dec[:, :, :, -H:, -W:] = weights * lower_right + (1 - weights) * area
         return dec
+
+    def tiled_encode(self, x):
+        """autoencoder_magvit.py:339-379: moments of overlapping 384-pixel tiles, blended in latent space."""
+        ts, tl = self.tile_sample_min_size, self.tile_latent_min_size
+        overlap_size = int(ts * (1 - self.tile_overlap_factor))
+        blend_extent = int(tl * self.tile_overlap_factor)
+        row_limit = tl - blend_extent
+        rows = []
+        for i in range(0, x.shape[3], overlap_size):
+            row = []
+            for j in range(0, x.shape[4], overlap_size):
+                row.append(self.quant_conv(self.encoder(x[:, :, :, i:i + ts, j:j + ts])))
+            rows.append(row)
+        result_rows = []
+        for i, row in enumerate(rows):
+            result_row = []
+            for j, tile in enumerate(row):
+                if i > 0:
+                    tile = self.blend_v(rows[i - 1][j], tile, blend_extent)
+                if j > 0:
+                    tile = self.blend_h(row[j - 1], tile, blend_extent)
+                result_row.append(tile[:, :, :, :row_limit, :row_limit])
+            result_rows.append(torch.cat(result_row, dim=4))
+        return torch.cat(result_rows, dim=3)
+
+    def encode_moments(self, x):
+        """autoencoder_magvit.py:230-269: the moments tensor [B, 2*latent, T', h, w] (mean | logvar) the reference wraps in
+        DiagonalGaussianDistribution; `.mode()` is its first half."""
+        ts = self.tile_sample_min_size
+        if self.use_tiling and (x.shape[-1] > ts or x.shape[-2] > ts):
+            return self.tiled_encode(x)
+        return self.quant_conv(self.encoder(x))
 
     def decode(self, z):
         tl = self.tile_latent_min_size

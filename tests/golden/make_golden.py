@@ -87,6 +87,25 @@ def make_vae_tiled():
     print("vae_ref_tiled", tuple(tiled.shape), float((tiled - full).abs().max()))
 
 
+def make_vae_encode():
+    """The reference's AutoencoderKLMagvit.encode (autoencoder_magvit.py:230-269: chunked Encoder, first frame alone and
+    then 4 frames at a time, + quant_conv) and tiled_encode (:339-379): the moments tensor of the returned posterior."""
+    boc, seed = (64, 64, 128, 128), 41
+    ref = ref_vae.reference_autoencoder(block_out_channels=boc, use_tiling=False)
+    mine = vae.init_weights_(vae.OracleAutoencoderKLMagvit(block_out_channels=boc, with_encoder=True), seed)
+    ref.load_state_dict(mine.state_dict(), strict=True)
+    x = torch.randn(1, 3, 9, 40, 56, generator=torch.Generator().manual_seed(seed + 100))
+    with torch.no_grad():
+        moments = ref.encode(x).latent_dist.parameters
+        ref.use_tiling, ref.tile_sample_min_size, ref.tile_latent_min_size = True, 32, 4
+        moments_tiled = ref.encode(x).latent_dist.parameters
+    save_file({"x": x, "moments": moments.contiguous(), "moments_tiled32": moments_tiled.contiguous()},
+              os.path.join(HERE, "vae_ref_encode.safetensors"),
+              metadata={"source": "reference AutoencoderKLMagvit.encode / tiled_encode (fp32, CPU)", "seed": str(seed),
+                        "block_out_channels": str(boc)})
+    print("vae_ref_encode", tuple(moments.shape), float(moments.abs().max()))
+
+
 DIT_REF_CASES = {
     # name: (config overrides, (B, F, H, W, S_text), weight seed, inpaint channels)
     "dit_ref_t2v": (dict(), (2, 3, 8, 12, 40), 21, 0),
@@ -153,5 +172,6 @@ if __name__ == "__main__":
         raise SystemExit("/root/reference not present: golden VAE vectors can only be minted in the authoring container")
     make_vae()
     make_vae_tiled()
+    make_vae_encode()
     make_dit()
     make_dit_reference()

@@ -71,6 +71,31 @@ def test_vae_oracle_wrapper_matches_live_reference():
         torch.testing.assert_close(mine.decode(z)[0], ref.decode(z).sample, rtol=1e-4, atol=1e-4)
 
 
+def test_vae_oracle_encode_matches_reference_golden():
+    """encode / tiled_encode moments of the REFERENCE's AutoencoderKLMagvit (chunked Encoder: frame 0 alone, then four
+    frames at a time with cached context): the whole-sequence encoder oracle reproduces them (I2V conditioning prep,
+    SURVEY.md section 8(f) 'next' row - no CUDA path yet)."""
+    path = os.path.join(GOLD, "vae_ref_encode.safetensors")
+    t, meta = load_file(path), _meta(path)
+    boc = ast.literal_eval(meta["block_out_channels"])
+    m = vae.init_weights_(vae.OracleAutoencoderKLMagvit(block_out_channels=boc, with_encoder=True), int(meta["seed"]))
+    with torch.no_grad():
+        torch.testing.assert_close(m.encode_moments(t["x"]), t["moments"], rtol=1e-4, atol=1e-4)
+        m.use_tiling, m.tile_sample_min_size, m.tile_latent_min_size = True, 32, 4
+        torch.testing.assert_close(m.encode_moments(t["x"]), t["moments_tiled32"], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.skipif(not ref_vae.available(), reason="/root/reference only exists in the authoring container")
+def test_vae_oracle_encode_matches_live_reference():
+    boc = (64, 64, 128, 128)
+    ref = ref_vae.reference_autoencoder(block_out_channels=boc, use_tiling=False)
+    mine = vae.init_weights_(vae.OracleAutoencoderKLMagvit(block_out_channels=boc, with_encoder=True), 5)
+    ref.load_state_dict(mine.state_dict(), strict=True)  # all 244 keys, encoder included
+    x = torch.randn(1, 3, 5, 24, 40, generator=torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        torch.testing.assert_close(mine.encode_moments(x), ref.encode(x).latent_dist.parameters, rtol=1e-4, atol=1e-4)
+
+
 def test_vae_tiled_decode_oracle_shapes_and_seams():
     m = vae.init_weights_(vae.OracleAutoencoderKLMagvit(block_out_channels=(64, 64, 128, 128), use_tiling=True,
                                                         tile_sample_min_size=64, mid_block_use_attention=False), 9)
