@@ -598,7 +598,8 @@ static int launch_gemm2(const void* a, int64_t lda, const void* w, int64_t ldw, 
 // CTA pairs once there are at least four waves of 128x256 tiles (EA_GEMM_2SM=0 disables them: A/B measurements)
 static bool use_pairs(const GemmDevArgs& p) {
   static const bool enabled = [] { const char* e = getenv("EA_GEMM_2SM"); return !(e && e[0] == '0'); }();
-  return enabled && p.N >= 256 && (int64_t)((p.M + kBM - 1) / kBM) * ((p.N + 255) / 256) >= 4 * sm_count();
+  // (N a multiple of 256: every shape of the model; ragged widths stay on the one-CTA kernel)
+  return enabled && p.N % 256 == 0 && (int64_t)((p.M + kBM - 1) / kBM) * (p.N / 256) >= 4 * sm_count();
 }
 
 // ------------------------------------------------------------------------------------------------
