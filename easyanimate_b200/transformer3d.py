@@ -146,6 +146,17 @@ class EasyAnimateDiTBlock(nn.Module):
         return x_v, x_t
 
 
+def get_teacache_coefficients(model_name: str):
+    """transformer3d.py:124-137: polynomial that rescales the relative-L1 change, per released checkpoint family."""
+    name = model_name.lower()
+    if "v5.1-7b" in name:
+        return [1.07862322, -4.19362456, 3.06725828, 0.33161686, 0.02374758]
+    if "v5.1-12b" in name:
+        return [-10.47857366, 8.33844143, -0.78477557, 0.68798618, 0.0136149]
+    print(f"The model {model_name} is not supported by TeaCache.")
+    return None
+
+
 class TeaCache:
     """Timestep-embedding-aware step skipping, transformer3d.py:90-121: same counters, thresholds and polynomial
     rescale as the reference; `previous_modulated_input` / `previous_residual` are device tensors here."""
