@@ -208,7 +208,7 @@ EA_DEVICE uint32_t mapa_shared(uint32_t local_addr, uint32_t cta_rank) {  // sha
 }
 EA_DEVICE void mbar_arrive_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
   // default (.release.cta) semantics on purpose: `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR in front of every
-  // k-block's loads (7 % of all samples and a starved MMA thread in the first version, profiles/r01_ncu_gemm2_*); the
+  // k-block's loads (7 % of all samples and a starved MMA thread in the first version, profiles/r01_ncu_gemm2_first_version_summary.txt); the
   // producer publishes nothing through the generic proxy, the data arrives by TMA complete_tx
   asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
 }
