@@ -184,6 +184,25 @@ def test_dit_golden_regression():
     torch.testing.assert_close(sn[-200:], t["rope720_sin_tail"])
 
 
+@pytest.mark.skipif(not ref_dit.available(), reason="/root/reference only exists in the authoring container")
+def test_rope_crop_region_matches_reference_function():
+    """The RoPE grid's crop region (pipeline_easyanimate.py:82-97) is reference-owned code: its function is lifted out of
+    the pipeline file by AST (the file itself imports the text encoders) and compared with the oracle's and the product's
+    host-side restatements over every latent grid a 16-pixel-aligned video up to 1536 x 1536 can produce."""
+    import ast as _ast
+    from easyanimate_b200 import pipeline as prod
+    src = open(os.path.join(ref_dit.REFERENCE_ROOT, "easyanimate", "pipeline", "pipeline_easyanimate.py")).read()
+    fn = next(n for n in _ast.parse(src).body if isinstance(n, _ast.FunctionDef) and n.name == "get_resize_crop_region_for_grid")
+    ns = {}
+    exec(compile(_ast.Module(body=[fn], type_ignores=[]), "<reference>", "exec"), ns)
+    ref_fn = ns["get_resize_crop_region_for_grid"]
+    for gh in range(1, 97):
+        for gw in range(1, 97):
+            want = ref_fn((gh, gw), 45, 30)
+            assert dit.get_resize_crop_region_for_grid((gh, gw), 45, 30) == want
+            assert prod.get_resize_crop_region_for_grid((gh, gw), 45, 30) == want
+
+
 def test_rope_properties():
     cos, sin = dit.rope_for_video(720, 1280, 13)
     assert cos.shape == (13 * 45 * 80, 64) and cos.dtype == torch.float32
