@@ -80,3 +80,30 @@ def test_vae_config_surface_and_keys():
         AutoencoderKLMagvit(**dict(kw, cache_mag_vae=False))
     with pytest.raises(NotImplementedError):
         m.encode(torch.zeros(1))
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """Every argument struct of include/ea_b200.h, compiled by gcc, has the size and the field offsets of its ctypes
+    mirror in easyanimate_b200/_lib.py (same field names, same order): the binding cannot drift from the ABI silently."""
+    import subprocess
+    from easyanimate_b200 import _lib as L
+    pairs = {"ea_gemm_args": L.GemmArgs, "ea_qkv_args": L.QkvArgs, "ea_skinny_linear_args": L.SkinnyArgs,
+             "ea_ln_args": L.LnArgs, "ea_rmsnorm_args": L.RmsArgs, "ea_attn_args": L.AttnArgs, "ea_conv3d_args": L.ConvArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "ea_b200.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in pairs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+    # and the header declares no struct the binding does not mirror
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "ea_b200.h")).read(), flags=re.S)
+    assert sorted(re.findall(r"^\}\s*(ea_[a-z0-9_]+);", hdr, flags=re.M)) == sorted(pairs)
