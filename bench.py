@@ -340,7 +340,7 @@ def main():
                        "l2": ("inputs_exceed_L2" if act_bytes > 126e6 else "inputs_fit_L2 (not a timing configuration)") +
                              f" (one activation tensor of a forward is {act_bytes / 1e6:.0f} MB, weights {n_params * 2 / 1e9:.1f} GB)",
                        "tflop_per_step": flops_step / 1e12},
-            "model_tflops": flops_step * value / 1e12,
+            "model_tflops": flops_step * value / 1e12, "forwards_per_s": 2.0 * value,  # a CFG step is two MMDiT forwards
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": lat_host.numel() * 2 + emb_host.numel() * 2,
                     "d2h_bytes_per_step": out_host.numel() * 2},
             "gpu_launches": int(launches),
