@@ -2,7 +2,7 @@
 // CTA, one TMEM pass over the scores, per-tile MMA issuers, packed fp32x2 softmax, MUFU/FMA exp split) WITHOUT the
 // per-block row maximum on the hot path.
 //
-// ncu's warp-state samples on the fourth generation (profiles/r01_ncu_attn_v4d_source_hotspots.txt): a softmax warp
+// ncu's warp-state samples on the fourth generation (profiles/r01_ncu_attn_v4d_hotspots.txt): a softmax warp
 // spends only 54 % of a key block in the exp/pack/store phase; 8 % goes to the four dependent TMEM loads, 12 % to the
 // 65-instruction FMNMX3 chain that must finish before the first exponential can start, 6 % to o_done.  The softmax
 // result does not depend on WHICH reference value is subtracted, only on the same one being used for P and for the
