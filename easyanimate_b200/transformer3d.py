@@ -127,7 +127,7 @@ class EasyAnimateDiTBlock(nn.Module):
         w2, b2 = a_t.fused_qkv()
         ops.qkv_gemm_ln_rope(n_t, w2, b2, (a_t.norm_q.weight, a_t.norm_q.bias), (a_t.norm_k.weight, a_t.norm_k.bias),
                              None, ws.q, ws.k, ws.v, rows_per_batch=S_t, seq_offset=0, eps=a_t.norm_q.eps)
-        o_t, o_v = ops.attention(ws.q, ws.k, ws.v, S_t)
+        o_t, o_v = ops.attention(ws.q, ws.k, ws.v, S_t) if ws.sp is None else ws.sp.attention(ws.q, ws.k, ws.v, S_t)
         ops.gemm(o_v.view(B * S_v, d), self.attn1.to_out[0].weight, self.attn1.to_out[0].bias,
                  epilogue=L.EPI_BIAS_GATE_RES, residual=x_v, gate=mod[:, 2 * d:3 * d], rows_per_batch=S_v, out=x_v)
         ops.gemm(o_t.view(B * S_t, d), a_t.to_out[0].weight, a_t.to_out[0].bias,
@@ -190,8 +190,9 @@ class TeaCache:
 class _Workspace:
     """Per-forward activation buffers shared by all blocks (allocated once per call through torch's caching allocator)."""
 
-    def __init__(self, B, S_v, S_t, d, heads, ff_inner, device):
+    def __init__(self, B, S_v, S_t, d, heads, ff_inner, device, sp=None):
         self.B, self.S_v, self.S_t = B, S_v, S_t
+        self.sp = sp  # UlyssesAttention (sequence parallelism: S_v is then this rank's token count) or None
         S = S_v + S_t
         e = lambda *shape: torch.empty(shape, device=device, dtype=bf16)  # noqa: E731
         self.n_v, self.n_t = e(B * S_v, d), e(B * S_t, d)
@@ -276,6 +277,7 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
         self.norm_out = _AdaLayerNorm(time_embed_dim, 2 * d, norm_eps, norm_elementwise_affine)
         self.proj_out = nn.Linear(d, patch_size * patch_size * out_channels)
         self.teacache = None
+        self.sequence_parallel = None  # UlyssesAttention, see set_sequence_parallel_group
         self.gradient_checkpointing = False
         self._proj_w_cache: Optional[tuple] = None
 
@@ -284,6 +286,14 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
                         coefficients=(-10.47857366, 8.33844143, -0.78477557, 0.68798618, 0.0136149)):
         """transformer3d.py:1485-1491. The cache tensors stay on the device (the reference keeps them on the CPU)."""
         self.teacache = TeaCache(list(coefficients), num_steps, rel_l1_thresh=rel_l1_thresh)
+
+    def set_sequence_parallel_group(self, group):
+        """Ulysses sequence parallelism over the ranks of `group` for ONE video (the reference's xfuser `ulysses_degree`,
+        predict_t2v.py:56-60): every rank calls forward with the same inputs and gets the full output; video tokens and
+        attention heads must divide by the group size.  None restores single-GPU execution.  See sequence_parallel.py
+        for what has and has not been validated."""
+        from .sequence_parallel import UlyssesAttention
+        self.sequence_parallel = None if group is None else UlyssesAttention(group)
 
     def _set_gradient_checkpointing(self, module, value=False):
         self.gradient_checkpointing = value
@@ -369,6 +379,18 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
             cos, sin = image_rotary_emb
             rope = (cos.to(device=dev, dtype=torch.float32).contiguous(), sin.to(device=dev, dtype=torch.float32).contiguous())
 
+        # sequence parallelism: from here to the output projection every rank works on its slice of the video tokens
+        sp = self.sequence_parallel
+        S_v_full = S_v
+        if sp is not None:
+            if self.teacache is not None:
+                raise NotImplementedError("TeaCache with sequence parallelism needs an all-reduce of the rel-L1 sums")
+            s0, s1 = sp.local_range(S_v)
+            x_v = sp.shard_tokens(x_v, B, S_v)
+            if rope is not None:
+                rope = (rope[0][s0:s1].contiguous(), rope[1][s0:s1].contiguous())
+            S_v = s1 - s0
+
         # 4. transformer blocks (transformer3d.py:1639-1671)
         ff_inner = self.transformer_blocks[0].ff.net[2].weight.shape[1] if len(self.transformer_blocks) else 4 * d
         # TeaCache decision (transformer3d.py:1563-1586): relative-L1 change of block 0's modulated video input
@@ -398,7 +420,7 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
             y = ops.ew_add(x_v, tc.previous_residual)
         else:
             ori = x_v.clone() if tc is not None else None  # (device copy; the blocks update x_v in place)
-            ws = _Workspace(B, S_v, S_t, d, self.num_heads, ff_inner, dev)
+            ws = _Workspace(B, S_v, S_t, d, self.num_heads, ff_inner, dev, sp=sp)
             for block in self.transformer_blocks:
                 x_v, x_t = block(x_v, x_t, temb, rope, ws)
 
@@ -411,6 +433,9 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
             if tc is not None:
                 tc.previous_residual = ops.ew_add(y, ori, subtract=True)  # transformer3d.py:1634
         z = ops.gemm(y, self.proj_out.weight, self.proj_out.bias)  # [B*S_v, p*p*C_out]
+        if sp is not None:
+            z = sp.gather_tokens(z, B, S_v)  # every rank gets all S_v_full tokens back
+            assert z.shape[0] == B * S_v_full
 
         # 6. unpatchify (transformer3d.py:1683-1685); like the reference, the output channel count is taken from the
         #    input latent (`channels`), which equals out_channels for every released model.

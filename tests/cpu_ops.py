@@ -1,0 +1,148 @@
+"""Torch (CPU) stand-ins for the entry points of easyanimate_b200.ops that EasyAnimateTransformer3DModel.forward calls, with
+the argument conventions of the real wrappers (shapes, in-place outputs, row-per-batch gates, head-major q/k/v, patchify
+column order) and the rounding points documented in include/ea_b200.h.  TEST INFRASTRUCTURE: they let the CPU suite run the
+product module's HOST LOGIC (buffer plumbing, stream split, sequence-parallel sharding) end to end without a GPU; they are
+never used by the product path."""
+import math
+
+import torch
+
+bf16 = torch.bfloat16
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RES, EPI_SCALE_F32, EPI_BIAS_RES = 0, 1, 2, 3, 4
+
+
+def _r(x):  # one bf16 rounding point
+    return x.to(bf16).float()
+
+
+def gemm(a, w, bias=None, *, epilogue=EPI_BIAS, out=None, residual=None, gate=None, rows_per_batch=0, scale=1.0):
+    acc = a.float() @ w.float().t()
+    if epilogue == EPI_SCALE_F32:
+        y = acc * scale
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y
+    y = _r(acc + (bias.float() if bias is not None else 0.0))
+    if epilogue == EPI_BIAS_GELU:
+        y = _r(torch.nn.functional.gelu(y, approximate="tanh"))
+    elif epilogue == EPI_BIAS_GATE_RES:
+        batch = torch.arange(a.shape[0]) // rows_per_batch
+        y = _r(residual.float() + _r(gate.float()[batch] * y))
+    elif epilogue == EPI_BIAS_RES:
+        y = _r(y + residual.float())
+    y = y.to(bf16)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def skinny_linear(x, w, bias, *, act_in=0, act_out=0):
+    xf = x.float()
+    if act_in:
+        xf = _r(torch.nn.functional.silu(xf))
+    y = _r(xf @ w.float().t() + (bias.float() if bias is not None else 0.0))
+    if act_out:
+        y = _r(torch.nn.functional.silu(y))
+    return y.to(bf16)
+
+
+def layernorm_modulate(x, w, b, eps, *, shift=None, scale=None, rows_per_batch=0, pre=None, out=None):
+    d = x.shape[1]
+    y = x.float()
+    if pre is not None:
+        y = _r(torch.nn.functional.layer_norm(y, (d,), pre[0].float(), pre[1].float(), pre[2]))
+    y = torch.nn.functional.layer_norm(y, (d,), None if w is None else w.float(), None if b is None else b.float(), eps)
+    y = _r(y)
+    if shift is not None:
+        batch = torch.arange(x.shape[0]) // rows_per_batch
+        y = _r(_r(y * (1 + scale.float()[batch])) + shift.float()[batch])
+    y = y.to(bf16)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def rmsnorm(x, w, eps):
+    xf = x.float()
+    y = _r(xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps))
+    return (w.float() * y).to(bf16)
+
+
+def timestep_embedding(t, dim, flip_sin_to_cos=True, freq_shift=0.0):
+    half = dim // 2
+    exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32) / (half - freq_shift)
+    emb = t.float()[:, None] * torch.exp(exponent)[None, :]
+    emb = torch.cat([torch.sin(emb), torch.cos(emb)], dim=-1)
+    if flip_sin_to_cos:
+        emb = torch.cat([emb[:, half:], emb[:, :half]], dim=-1)
+    return emb.to(bf16)
+
+
+def patchify(x, x2=None):
+    if x2 is not None:
+        x = torch.cat([x, x2], dim=1)
+    B, C, F, H, W = x.shape
+    a = x.view(B, C, F, H // 2, 2, W // 2, 2).permute(0, 2, 3, 5, 1, 4, 6).reshape(B * F * (H // 2) * (W // 2), C * 4)
+    ldk = (4 * C + 7) // 8 * 8
+    out = torch.zeros((a.shape[0], ldk), dtype=bf16)
+    out[:, :4 * C] = a
+    return out
+
+
+def unpatchify(y, B, C, F, H, W):
+    t = y[:, :4 * C].reshape(B, F, H // 2, W // 2, C, 2, 2)
+    return t.permute(0, 4, 1, 2, 5, 3, 6).reshape(B, C, F, H, W).contiguous().to(bf16)
+
+
+def qkv_gemm_ln_rope(a, w_qkv, b_qkv, ln_q, ln_k, rope, q, k, v, *, rows_per_batch, seq_offset, eps=1e-6):
+    M, d = a.shape
+    B, H = q.shape[0], q.shape[1]
+    y = _r(a.float() @ w_qkv.float().t() + b_qkv.float()).view(B, rows_per_batch, 3, H, 64)
+    qq, kk, vv = y[:, :, 0], y[:, :, 1], y[:, :, 2]  # [B, rows, H, 64]
+    qq = _r(torch.nn.functional.layer_norm(qq, (64,), ln_q[0].float(), ln_q[1].float(), eps))
+    kk = _r(torch.nn.functional.layer_norm(kk, (64,), ln_k[0].float(), ln_k[1].float(), eps))
+    if rope is not None:
+        cos, sin = rope[0][None, :, None, :], rope[1][None, :, None, :]
+
+        def rot(t):
+            tr = t.reshape(*t.shape[:-1], 32, 2)
+            rotated = torch.stack([-tr[..., 1], tr[..., 0]], dim=-1).flatten(-2)
+            return _r(t * cos + rotated * sin)
+
+        qq, kk = rot(qq), rot(kk)
+    sl = slice(seq_offset, seq_offset + rows_per_batch)
+    q[:, :, sl] = qq.permute(0, 2, 1, 3).to(bf16)
+    k[:, :, sl] = kk.permute(0, 2, 1, 3).to(bf16)
+    v[:, :, sl] = vv.permute(0, 2, 1, 3).to(bf16)
+
+
+def attention(q, k, v, S_text, *, scale=None, variant=0):
+    B, H, S, hd = q.shape
+    o = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float(), scale=scale)
+    o = o.transpose(1, 2).reshape(B, S, H * hd).to(bf16)
+    return o[:, :S_text].contiguous(), o[:, S_text:].contiguous()
+
+
+def ew_add(a, b, out=None, subtract=False):
+    y = (a.float() - b.float() if subtract else a.float() + b.float()).to(bf16)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def rel_l1_distance(cur, prev):
+    num = (cur.float() - prev.float()).to(bf16).float().abs().mean().to(bf16)
+    den = prev.float().abs().mean().to(bf16)
+    return float((num / den).item())
+
+
+def install(monkeypatch):
+    """Route easyanimate_b200.ops (as seen by transformer3d) to the stand-ins above."""
+    from easyanimate_b200 import ops
+    for name in ("gemm", "skinny_linear", "layernorm_modulate", "rmsnorm", "timestep_embedding", "patchify", "unpatchify",
+                 "qkv_gemm_ln_rope", "attention", "ew_add", "rel_l1_distance"):
+        monkeypatch.setattr(ops, name, globals()[name])

@@ -1,0 +1,62 @@
+"""The product module's HOST LOGIC on CPU: EasyAnimateTransformer3DModel.forward (buffer plumbing, text/video stream split,
+in-place gated residuals, I2V channel concat, TeaCache bookkeeping) run end to end with torch stand-ins for the CUDA entry
+points (tests/cpu_ops.py) and compared with the oracle - no kernel is exercised here, the GPU suite does that."""
+import pytest
+import torch
+
+from oracle import dit
+from tests import cpu_ops
+
+bf16 = torch.bfloat16
+CFG = dict(num_attention_heads=2, attention_head_dim=64, in_channels=16, out_channels=16, patch_size=2, num_layers=2,
+           time_embed_dim=64, add_norm_text_encoder=True, text_embed_dim=128, text_embed_dim_t5=None)
+
+
+def _models(cfg, seed=11):
+    from easyanimate_b200.transformer3d import EasyAnimateTransformer3DModel
+    ob = dit.init_weights_(dit.OracleTransformer3D(**cfg), seed).to(bf16)
+    ours = EasyAnimateTransformer3DModel(**cfg).to(bf16)
+    ours.load_state_dict(ob.state_dict(), strict=True)
+    return ob, ours
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm()).item()
+
+
+@pytest.mark.parametrize("inpaint", [False, True])
+def test_forward_host_logic_matches_oracle(monkeypatch, inpaint):
+    cpu_ops.install(monkeypatch)
+    cfg = dict(CFG, in_channels=33) if inpaint else CFG
+    ob, ours = _models(cfg)
+    g = torch.Generator().manual_seed(2)
+    lat = torch.randn(2, 16, 3, 8, 12, generator=g).to(bf16)
+    enc = (torch.randn(2, 9, 128, generator=g) * 3).to(bf16)
+    inp = torch.randn(2, 17, 3, 8, 12, generator=g).to(bf16) if inpaint else None
+    t = torch.tensor([937.0, 421.0]).to(bf16)
+    rope = dit.rope_for_video(64, 96, 3)
+    with torch.no_grad():
+        ref = ob(lat, t, encoder_hidden_states=enc, image_rotary_emb=rope, inpaint_latents=inp)[0]
+        got = ours(lat, t, encoder_hidden_states=enc, image_rotary_emb=rope, inpaint_latents=inp, return_dict=False)[0]
+    assert got.shape == ref.shape == (2, 16, 3, 8, 12)
+    assert _rel(got, ref) < 2e-2  # bf16 round-off of two different op orders; a plumbing error is O(1)
+
+
+def test_teacache_host_logic_matches_oracle(monkeypatch):
+    cpu_ops.install(monkeypatch)
+    ob, ours = _models(CFG)
+    coeffs = [1.07862322, -4.19362456, 3.06725828, 0.33161686, 0.02374758]
+    ob.teacache = dit.OracleTeaCache(coeffs, 6, 0.08)
+    ours.enable_teacache(6, 0.08, coefficients=coeffs)
+    g = torch.Generator().manual_seed(4)
+    lat = torch.randn(2, 16, 3, 8, 12, generator=g).to(bf16)
+    enc = (torch.randn(2, 9, 128, generator=g) * 3).to(bf16)
+    rope = dit.rope_for_video(64, 96, 3)
+    with torch.no_grad():
+        for i in range(6):
+            x, t = (lat.float() * (1.0 - 0.01 * i)).to(bf16), torch.tensor([900.0 - 30 * i] * 2).to(bf16)
+            ref = ob(x, t, encoder_hidden_states=enc, image_rotary_emb=rope)[0]
+            got = ours(x, t, encoder_hidden_states=enc, image_rotary_emb=rope, return_dict=False)[0]
+            assert _rel(got, ref) < 3e-2, i
+    assert ours.teacache.cnt == 0 and ob.teacache.cnt == 0  # both wrapped around after num_steps calls
+    assert ob.teacache.skipped >= 1 and ours.teacache.skipped == ob.teacache.skipped  # the cached path is exercised, same decisions

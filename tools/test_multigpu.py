@@ -1,5 +1,6 @@
 """2-GPU checks (run under torchrun on a B200 box): CFG-parallel sampler == single-GPU batch-of-2 step; tile-parallel
-VAE tiled_decode == single-GPU tiled_decode.  Usage:
+VAE tiled_decode == single-GPU tiled_decode; with EA_TEST_SP=1 also Ulysses sequence-parallel forward vs the single-GPU
+forward (reported, not yet part of `ok`: it has not run on GPUs).  Usage:
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/test_multigpu.py
 """
 import os
@@ -42,6 +43,16 @@ def main():
         b = pair.step(b, i, emb, rope)
     torch.cuda.synchronize()
     d1 = (a.float() - b.float()).abs().max().item()
+    # ---- DiT: Ulysses sequence parallelism over the same ranks vs the single-GPU forward (first GPU run: round 2)
+    d3 = None
+    if os.environ.get("EA_TEST_SP", "0") == "1":
+        t = torch.tensor([937.0], device=dev).to(bf16)
+        one = model(lat, t, encoder_hidden_states=emb[:1], image_rotary_emb=rope, return_dict=False)[0]
+        model.set_sequence_parallel_group(grp)
+        sp = model(lat, t, encoder_hidden_states=emb[:1], image_rotary_emb=rope, return_dict=False)[0]
+        model.set_sequence_parallel_group(None)
+        torch.cuda.synchronize()
+        d3 = (one.float() - sp.float()).abs().max().item()
     # ---- VAE: tile-parallel tiled decode vs single-GPU tiled decode
     with torch.device(dev):
         vae = AutoencoderKLMagvit(latent_channels=16, cache_mag_vae=True, spatial_group_norm=True,
@@ -64,7 +75,8 @@ def main():
     ok = torch.tensor([float(d1 == 0.0 and d2 == 0.0 and bool(torch.isfinite(par).all()))], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print({"cfg_parallel_max_abs_diff": d1, "tile_parallel_max_abs_diff": d2, "shape": tuple(par.shape), "ok": bool(ok.item())})
+        print({"cfg_parallel_max_abs_diff": d1, "tile_parallel_max_abs_diff": d2, "sequence_parallel_max_abs_diff": d3,
+               "shape": tuple(par.shape), "ok": bool(ok.item())})
     dist.destroy_process_group()
     sys.exit(0 if ok.item() else 1)
 
