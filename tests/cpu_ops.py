@@ -146,3 +146,87 @@ def install(monkeypatch):
     for name in ("gemm", "skinny_linear", "layernorm_modulate", "rmsnorm", "timestep_embedding", "patchify", "unpatchify",
                  "qkv_gemm_ln_rope", "attention", "ew_add", "rel_l1_distance"):
         monkeypatch.setattr(ops, name, globals()[name])
+
+
+# -----------------------------------------------------------------------------------------------------------------------
+# VAE entry points (easyanimate_b200.vae_ops): channels-last [T,H,W,C] activations for one batch element
+# -----------------------------------------------------------------------------------------------------------------------
+def conv3d_causal(x, w_packed, bias, cout, *, residual=None, dup_frames=False, out_planar=False):
+    T, H, W, Cin = x.shape
+    w = w_packed.float().view(w_packed.shape[0], 3, 3, 3, Cin).permute(0, 4, 1, 2, 3)[:cout]  # [cout,Cin,kt,kh,kw]
+    xin = x.float().permute(3, 0, 1, 2)[None]  # [1,Cin,T,H,W]
+    xin = torch.nn.functional.pad(xin, (0, 0, 0, 0, 2, 0), mode="replicate")
+    y = torch.nn.functional.conv3d(xin, w, bias.float()[:cout], padding=(0, 1, 1))[0]  # [cout,T,H,W]
+    y = _r(y)
+    if residual is not None:
+        y = _r(y + residual.float().permute(3, 0, 1, 2))
+    if dup_frames and T > 1:
+        idx = [0] + [i for t in range(1, T) for i in (t, t)]
+        y = y[:, idx]
+    y = y.to(bf16)
+    return y.contiguous() if out_planar else y.permute(1, 2, 3, 0).contiguous()
+
+
+def prepare_latents(z, w, b, cpad=64):
+    Cc, T, H, W = z.shape
+    y = _r(torch.einsum("oc,cthw->othw", w.float().reshape(Cc, Cc), z.float()) + b.float()[:, None, None, None])
+    out = torch.zeros((T, H, W, cpad), dtype=bf16)
+    out[..., :Cc] = y.permute(1, 2, 3, 0)
+    return out
+
+
+def groupnorm(x, gamma, beta, groups, eps, silu):
+    T, H, W, C = x.shape
+    y = torch.nn.functional.group_norm(x.float().permute(0, 3, 1, 2), groups, gamma.float(), beta.float(), eps)  # per frame
+    y = _r(y)
+    if silu:
+        y = _r(torch.nn.functional.silu(y))
+    return y.permute(0, 2, 3, 1).contiguous().to(bf16)
+
+
+def upsample2x(x):
+    return x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2).contiguous()
+
+
+def spatial_attention(n, w_qkv, b_qkv, w_out, b_out, residual, frames, scale):
+    M, C = n.shape
+    HW = M // frames
+    qkv = _r(n.float() @ w_qkv.float().t() + b_qkv.float()).view(frames, HW, 3, C)
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    p = _r(torch.softmax(q @ k.transpose(1, 2) * scale, dim=-1))
+    o = _r(p @ v).reshape(M, C)
+    return _r(_r(o @ w_out.float().t() + b_out.float()) + residual.float()).to(bf16)
+
+
+def tile_blend(a, b, extent, axis):
+    if axis == 0:
+        extent = min(a.shape[3], b.shape[3], extent)
+        for y in range(extent):
+            b[:, :, :, y, :] = (_r(a[:, :, :, -extent + y, :].float() * (1 - y / extent)) +
+                                _r(b[:, :, :, y, :].float() * (y / extent))).to(bf16)
+    else:
+        extent = min(a.shape[4], b.shape[4], extent)
+        for x in range(extent):
+            b[:, :, :, :, x] = (_r(a[:, :, :, :, -extent + x].float() * (1 - x / extent)) +
+                                _r(b[:, :, :, :, x].float() * (x / extent))).to(bf16)
+
+
+def copy2d(src, dst, rows, cols, dst_r0, dst_c0):
+    dst[..., dst_r0:dst_r0 + rows, dst_c0:dst_c0 + cols] = src[..., :rows, :cols]
+
+
+def corner_blend(src, dst):
+    Hc, Wc = src.shape[3], src.shape[4]
+    wx = torch.linspace(0, 1, Wc).unsqueeze(0).repeat(Hc, 1)
+    wy = torch.linspace(0, 1, Hc).unsqueeze(1).repeat(1, Wc)
+    wgt = torch.min(wx, wy)[None, None, None]
+    area = dst[..., -Hc:, -Wc:].float()
+    dst[..., -Hc:, -Wc:] = (wgt * src.float() + (1 - wgt) * area).to(bf16)
+
+
+def install_vae(monkeypatch):
+    from easyanimate_b200 import ops, vae_ops
+    for name in ("conv3d_causal", "prepare_latents", "groupnorm", "upsample2x", "spatial_attention", "tile_blend", "copy2d",
+                 "corner_blend"):
+        monkeypatch.setattr(vae_ops, name, globals()[name])
+    monkeypatch.setattr(ops, "gemm", gemm)
