@@ -230,3 +230,14 @@ def install_vae(monkeypatch):
                  "corner_blend"):
         monkeypatch.setattr(vae_ops, name, globals()[name])
     monkeypatch.setattr(ops, "gemm", gemm)
+
+
+def cfg_euler_step(noise_pred, latents, guidance_scale, sigma, sigma_next, use_cfg=True):
+    """include/ea_b200.h ea_cfg_euler_step: v = u + g*(c-u) in bf16 ops; x_out = bf16(float(x) + bf16(bf16(dt) * v))."""
+    if use_cfg:
+        u, c = noise_pred.chunk(2)
+        v = u + guidance_scale * (c - u)  # bf16 tensor ops, like the reference
+    else:
+        v = noise_pred
+    dt = torch.tensor(sigma_next - sigma, dtype=torch.float32).to(bf16)
+    return (latents.float() + (dt * v).float()).to(bf16)
