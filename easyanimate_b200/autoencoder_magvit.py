@@ -9,7 +9,11 @@ layer (the reference's per-latent-frame loop with conv caches, omnigen_enc_dec.p
 arithmetically the same convolution), per-frame GroupNorm+SiLU kernels, tcgen05 GEMMs for the 1x1x1 shortcuts and
 the mid-block spatial attention.
 
-``encode`` is a SURVEY.md §8(f) "next" row and raises NotImplementedError.
+``encode`` (I2V / inpaint conditioning prep) runs on the SAME validated kernels: the
+encoder's stride-2 convolutions (downsamplers.py:24-96) are executed as the stride-1 causal convolution followed by a
+strided pick (output (t, i, j) of the strided conv == output (2t, 2i+1, 2j+1) of the stride-1 one), which wastes 4-8x of
+the FLOPs of those three layers but needs no new kernel.  STATUS: host logic checked on CPU against the oracle, which is
+pinned to the reference's Encoder (tests/test_host_logic_cpu.py); first GPU run pending (tests/test_zz_vae_encode_gpu.py).
 """
 from __future__ import annotations
 
@@ -21,11 +25,14 @@ import torch.nn as nn
 
 from . import _lib as L
 from . import ops, vae_ops
-from .config import ConfigMixinLite, DecoderOutput, capture_init_config, load_state_dict_from_dir
+from .config import (AutoencoderKLOutput, ConfigMixinLite, DecoderOutput, DiagonalGaussianDistribution, capture_init_config,
+                     load_state_dict_from_dir)
 
 bf16 = torch.bfloat16
 
 DEFAULT_UP_BLOCKS = ("SpatialUpBlock3D", "SpatialTemporalUpBlock3D", "SpatialTemporalUpBlock3D", "SpatialTemporalUpBlock3D")
+DEFAULT_DOWN_BLOCKS = ("SpatialDownBlock3D", "SpatialTemporalDownBlock3D", "SpatialTemporalDownBlock3D",
+                       "SpatialTemporalDownBlock3D")
 
 
 def str_eval(item):
@@ -179,6 +186,65 @@ class _Decoder(nn.Module):  # omnigen_enc_dec.py:339-677
         return self.conv_out.run(x, out_planar=True)
 
 
+class _Downsampler(nn.Module):  # downsamplers.py:24-46 (spatial), :74-96 (spatial + temporal)
+    def __init__(self, channels, temporal):
+        super().__init__()
+        self.conv = _PackedConv(channels, channels)
+        self.temporal = temporal
+
+    def run(self, x):
+        # CausalConv3d(kernel 3, stride (s_t, 2, 2), no spatial padding) after F.pad(x, (0,1,0,1)): output (t,i,j) reads
+        # frames 2t-2..2t (clamped at 0) and pixels 2i..2i+2 / 2j..2j+2 with zeros past the right/bottom edge - exactly
+        # output (s_t*t, 2i+1, 2j+1) of the stride-1 causal convolution with 1-pixel zero padding that the kernel computes.
+        y = self.conv.run(x)
+        if self.temporal:
+            y = y[::2]
+        return y[:, 1::2, 1::2].contiguous()
+
+
+class _DownBlock(nn.Module):  # down_blocks.py:156-212, 272-328
+    def __init__(self, cin, cout, num_layers, add_downsample, temporal, groups):
+        super().__init__()
+        self.convs = nn.ModuleList([_ResBlock(cin if i == 0 else cout, cout, groups) for i in range(num_layers)])
+        self.downsampler = _Downsampler(cout, temporal) if add_downsample else None
+
+    def run(self, x):
+        for c in self.convs:
+            x = c.run(x)
+        if self.downsampler is not None:
+            x = self.downsampler.run(x)
+        return x
+
+
+class _Encoder(nn.Module):  # omnigen_enc_dec.py:24-337
+    def __init__(self, in_channels, latent_channels, down_block_types, block_out_channels, layers_per_block, norm_num_groups,
+                 mid_block_use_attention):
+        super().__init__()
+        self.conv_in = _PackedConv(in_channels, block_out_channels[0], cin_pad=64)
+        self.down_blocks = nn.ModuleList([])
+        out_ch = block_out_channels[0]
+        for i, typ in enumerate(down_block_types):
+            if typ not in ("SpatialDownBlock3D", "SpatialTemporalDownBlock3D"):
+                raise NotImplementedError(f"down block type {typ} is not used by the v5/v5.1 VAE")
+            in_ch, out_ch = out_ch, block_out_channels[i]
+            final = i == len(block_out_channels) - 1
+            self.down_blocks.append(_DownBlock(in_ch, out_ch, layers_per_block, not final,
+                                               typ == "SpatialTemporalDownBlock3D", norm_num_groups))
+        self.mid_block = _MidBlock(block_out_channels[-1], layers_per_block, mid_block_use_attention, norm_num_groups)
+        self.conv_norm_out = nn.GroupNorm(norm_num_groups, block_out_channels[-1], eps=1e-6)
+        self.conv_out = _PackedConv(block_out_channels[-1], 2 * latent_channels, cout_pad=32)
+
+    def run(self, x):
+        """x [T,H,W,64] channels-last (RGB in the first 3 channels) -> planar [2*latent, T', H/8, W/8]."""
+        x = self.conv_in.run(x)
+        for down in self.down_blocks:
+            x = down.run(x)
+        x = self.mid_block.run(x)
+        n = self.conv_norm_out
+        x = vae_ops.groupnorm(x, n.weight, n.bias, n.num_groups, n.eps, True)
+        return self.conv_out.run(x, out_planar=True)
+
+
 class AutoencoderKLMagvit(nn.Module, ConfigMixinLite):
     _supports_gradient_checkpointing = False
 
@@ -237,6 +303,13 @@ class AutoencoderKLMagvit(nn.Module, ConfigMixinLite):
                                 norm_num_groups, mid_block_use_attention, mid_block_attention_type)
         self.quant_conv = nn.Conv3d(2 * latent_channels, 2 * latent_channels, kernel_size=1)
         self.post_quant_conv = nn.Conv3d(latent_channels, latent_channels, kernel_size=1)
+        down_block_types = str_eval(down_block_types) or DEFAULT_DOWN_BLOCKS
+        if 2 * latent_channels > 32 or in_channels > 32:
+            raise NotImplementedError("encode needs 2*latent_channels <= 32 and in_channels <= 32")
+        # registered after the decode side: module order (and with it any seeded init loop over named_parameters) of the
+        # decoder is what it was before the encoder existed
+        self.encoder = _Encoder(in_channels, latent_channels, down_block_types, list(block_out_channels), layers_per_block,
+                                norm_num_groups, mid_block_use_attention)
         self.slice_mag_vae = slice_mag_vae
         self.slice_compression_vae = slice_compression_vae
         self.cache_compression_vae = cache_compression_vae
@@ -349,9 +422,62 @@ class AutoencoderKLMagvit(nn.Module, ConfigMixinLite):
             return (decoded,)
         return DecoderOutput(sample=decoded)
 
-    def encode(self, x, return_dict: bool = True):
-        raise NotImplementedError("AutoencoderKLMagvit.encode is a SURVEY.md §8(f) 'next' row (I2V conditioning prep) and "
-                                  "is not implemented in this round")
+    # ---- encode (I2V / inpaint conditioning prep) ---------------------------------------------------------------
+    def _encode_one(self, x: torch.Tensor) -> torch.Tensor:
+        """x [C_in,T,H,W] planar bf16 -> moments planar [1, 2*latent, T', H/8, W/8]: Encoder + quant_conv
+        (autoencoder_magvit.py:262-265).  T must be 1 + 4m (the reference's chunking, omnigen_enc_dec.py:283-290)."""
+        cin = x.shape[0]
+        if (x.shape[1] - 1) % 4:
+            raise ValueError(f"encode needs 1 + 4m frames (the reference encodes frame 0 and then 4 frames at a time), got {x.shape[1]}")
+        eye = torch.eye(cin, device=x.device, dtype=bf16)
+        xin = vae_ops.prepare_latents(x, eye, torch.zeros(cin, device=x.device, dtype=bf16), 64)  # planar -> [T,H,W,64]
+        h = self.encoder.run(xin)                                   # planar [2L, T', h, w]
+        qc = self.quant_conv
+        m = vae_ops.prepare_latents(h, qc.weight, qc.bias, h.shape[0])  # 1x1x1 conv -> channels-last [T', h, w, 2L]
+        return m.permute(3, 0, 1, 2).unsqueeze(0).contiguous()
+
+    def _tiled_encode_one(self, x: torch.Tensor) -> torch.Tensor:
+        """autoencoder_magvit.py:339-379 for one batch element: overlapping tiles encoded separately, moments blended."""
+        ts, tl = self.tile_sample_min_size, self.tile_latent_min_size
+        overlap_size = int(ts * (1 - self.tile_overlap_factor))
+        blend_extent = int(tl * self.tile_overlap_factor)
+        row_limit = tl - blend_extent
+        rows = [[self._encode_one(x[:, :, i:i + ts, j:j + ts].contiguous()) for j in range(0, x.shape[3], overlap_size)]
+                for i in range(0, x.shape[2], overlap_size)]
+        widths = [min(t.shape[4], row_limit) for t in rows[0]]
+        heights = [min(r[0].shape[3], row_limit) for r in rows]
+        out = torch.empty((1, rows[0][0].shape[1], rows[0][0].shape[2], sum(heights), sum(widths)), device=x.device, dtype=bf16)
+        r0 = 0
+        for i, row in enumerate(rows):
+            c0 = 0
+            for j, tile in enumerate(row):
+                if i > 0:
+                    vae_ops.tile_blend(rows[i - 1][j], tile, blend_extent, 0)
+                if j > 0:
+                    vae_ops.tile_blend(row[j - 1], tile, blend_extent, 1)
+                vae_ops.copy2d(tile, out, heights[i], widths[j], r0, c0)
+                c0 += widths[j]
+            r0 += heights[i]
+        return out
+
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor, return_dict: bool = True):
+        """autoencoder_magvit.py:229-269: x [B,3,T,H,W] in [-1,1] -> posterior over [B,latent,T',H/8,W/8] (T = 1 + 4m)."""
+        if self.upcast_vae:
+            raise NotImplementedError("upcast_vae (fp32 encode) is not implemented: easyanimate_b200 computes in bf16")
+        if self.dtype != bf16:
+            raise L.EaError("easyanimate_b200 computes in bf16: call .to(torch.bfloat16) on the module first")
+        if not x.is_cuda:
+            raise L.EaError("easyanimate_b200 has no CPU path: the video must be on a CUDA device")
+        x = x.to(bf16)
+        ts = self.tile_sample_min_size
+        tiled = (self.use_tiling or self.use_tiling_encoder) and (x.shape[-1] > ts or x.shape[-2] > ts)
+        outs = [(self._tiled_encode_one(xb) if tiled else self._encode_one(xb.contiguous())) for xb in x]
+        moments = outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+        posterior = DiagonalGaussianDistribution(moments)
+        if not return_dict:
+            return (posterior,)
+        return AutoencoderKLOutput(latent_dist=posterior)
 
     def _clear_conv_cache(self):  # the whole-sequence kernels keep no cache; kept for API compatibility
         return None
@@ -359,7 +485,8 @@ class AutoencoderKLMagvit(nn.Module, ConfigMixinLite):
     # ----------------------------------------------------------------------------------------------------------
     @classmethod
     def from_pretrained(cls, pretrained_model_path, subfolder=None, **vae_additional_kwargs):
-        """autoencoder_magvit.py:478-505 (decoder-side keys; encoder weights in the checkpoint are ignored)."""
+        """autoencoder_magvit.py:478-505: every key of the released checkpoint has a home (encoder, quant_conv, post_quant_conv,
+        decoder); tensors whose shape does not match are skipped like the reference does."""
         if subfolder is not None:
             pretrained_model_path = os.path.join(pretrained_model_path, subfolder)
         config = cls.load_config(pretrained_model_path)

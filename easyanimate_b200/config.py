@@ -89,6 +89,35 @@ class DecoderOutput:
         return (self.sample,)[i]
 
 
+class DiagonalGaussianDistribution:
+    """The posterior object `vae.encode(x)[0]` returns in the reference (diffusers autoencoders/vae.py): `parameters` is the
+    moments tensor [B, 2*C, T, h, w] = (mean | logvar); the pipelines call `.sample()` or `.mode()` on it
+    (pipeline_easyanimate_inpaint.py:769-826).  Small host-side torch ops on the latent-sized tensor."""
+
+    def __init__(self, parameters: torch.Tensor, deterministic: bool = False):
+        self.parameters = parameters
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.deterministic = deterministic
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+
+    def sample(self, generator=None) -> torch.Tensor:
+        noise = torch.randn(self.mean.shape, generator=generator, device=self.parameters.device, dtype=self.parameters.dtype)
+        return self.mean + self.std * noise
+
+    def mode(self) -> torch.Tensor:
+        return self.mean
+
+
+@dataclass
+class AutoencoderKLOutput:
+    latent_dist: DiagonalGaussianDistribution
+
+    def __getitem__(self, i):
+        return (self.latent_dist,)[i]
+
+
 def load_state_dict_from_dir(path: str) -> Dict[str, torch.Tensor]:
     """safetensors / .bin loader used by from_pretrained(_2d) (transformer3d.py:1692-1809, autoencoder_magvit.py:478-505)."""
     import glob

@@ -73,13 +73,16 @@ def test_vae_config_surface_and_keys():
     assert m.config.block_out_channels == [64, 64, 128, 128]
     assert m.quant_conv.weight.ndim == 5 and m.cache_mag_vae and m.mini_batch_decoder == 1 and m.mini_batch_encoder == 4
     assert m.tile_latent_min_size == 48
-    ours = {k for k in m.state_dict() if k.startswith("decoder.") or k.startswith("post_quant_conv.")}
-    ref = {k for k in vae.OracleAutoencoderKLMagvit(block_out_channels=(64, 64, 128, 128)).state_dict()}
-    assert ours == ref
+    # every key of the reference's AutoencoderKLMagvit (244 for this architecture; the oracle is pinned to it key by key)
+    ref = set(vae.OracleAutoencoderKLMagvit(block_out_channels=(64, 64, 128, 128), with_encoder=True).state_dict())
+    assert set(m.state_dict()) == ref and len(ref) == 244
     with pytest.raises(NotImplementedError):
         AutoencoderKLMagvit(**dict(kw, cache_mag_vae=False))
-    with pytest.raises(NotImplementedError):
-        m.encode(torch.zeros(1))
+    from easyanimate_b200 import _lib as L
+    with pytest.raises(L.EaError, match="no CPU path"):
+        m.to(torch.bfloat16).encode(torch.zeros(1, 3, 5, 16, 16))
+    with pytest.raises(L.EaError, match="no CPU path"):
+        m.decode(torch.zeros(1, 16, 2, 4, 4))
 
 
 def test_ctypes_structs_match_the_header_layout(tmp_path):

@@ -119,3 +119,53 @@ def test_sampler_loop_host_logic_matches_oracle_denoise_loop(monkeypatch):
         got = sampler.sample(lat, pe, ne, height=64, width=96, num_inference_steps=3)
     got = got[0] if isinstance(got, (tuple, list)) else got
     assert got.shape == ref.shape and _rel(got, ref) < 3e-2
+
+
+def _encode_cpu(ours, x):
+    tiled = ours.use_tiling and max(x.shape[-2:]) > ours.tile_sample_min_size
+    outs = [(ours._tiled_encode_one(xb) if tiled else ours._encode_one(xb.contiguous())) for xb in x]
+    return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+
+
+def _vae_pair_enc(**kw):
+    from oracle import vae
+    from easyanimate_b200.autoencoder_magvit import AutoencoderKLMagvit
+    boc = [64, 64, 128, 128]
+    ob = vae.init_weights_(vae.OracleAutoencoderKLMagvit(block_out_channels=boc, with_encoder=True, **kw), 31).to(bf16)
+    ours = AutoencoderKLMagvit(latent_channels=16, cache_mag_vae=True, spatial_group_norm=True,
+                               mid_block_attention_type="spatial", block_out_channels=boc, **kw).to(bf16)
+    ours.load_state_dict(ob.state_dict(), strict=True)
+    return ob, ours
+
+
+def test_vae_encode_host_logic_matches_oracle(monkeypatch):
+    """encode: planar->channels-last, stride-2 convolutions as stride-1 + strided pick, mid block, conv_out, quant_conv."""
+    cpu_ops.install_vae(monkeypatch)
+    ob, ours = _vae_pair_enc()
+    x = torch.randn(1, 3, 9, 40, 56, generator=torch.Generator().manual_seed(7)).to(bf16)
+    with torch.no_grad():
+        ref = ob.encode_moments(x)
+        got = _encode_cpu(ours, x)
+    assert got.shape == ref.shape == (1, 32, 3, 5, 7)
+    assert _rel(got, ref) < 3e-2
+
+
+def test_vae_tiled_encode_host_logic_matches_oracle(monkeypatch):
+    cpu_ops.install_vae(monkeypatch)
+    ob, ours = _vae_pair_enc(use_tiling=True, tile_sample_min_size=32)
+    ob.tile_latent_min_size = ours.tile_latent_min_size  # 32 / 8
+    x = torch.randn(1, 3, 5, 40, 56, generator=torch.Generator().manual_seed(9)).to(bf16)
+    with torch.no_grad():
+        ref = ob.encode_moments(x)
+        got = _encode_cpu(ours, x)
+    assert got.shape == ref.shape == (1, 32, 2, 5, 7)
+    assert _rel(got, ref) < 3e-2
+
+
+def test_posterior_object_surface():
+    from easyanimate_b200.config import AutoencoderKLOutput, DiagonalGaussianDistribution
+    m = torch.randn(2, 32, 3, 4, 5)
+    d = DiagonalGaussianDistribution(m)
+    assert torch.equal(d.mode(), m[:, :16]) and d.sample(generator=torch.Generator().manual_seed(0)).shape == (2, 16, 3, 4, 5)
+    out = AutoencoderKLOutput(latent_dist=d)
+    assert out[0] is d and out.latent_dist.parameters is m

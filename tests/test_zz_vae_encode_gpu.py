@@ -1,0 +1,72 @@
+"""AutoencoderKLMagvit.encode on the GPU (I2V / inpaint conditioning prep).
+
+STATUS: written at the end of round 1, after the GPU budget of the round was spent - encode() composes kernels that are all
+validated elsewhere (tests/test_vae_gpu.py) and its host logic is checked on CPU against the oracle, which is pinned to the
+reference's Encoder (tests/test_host_logic_cpu.py, tests/test_oracle_cpu.py), but THESE tests have not run on a GPU yet.
+They are therefore non-strict xfail: a pass shows up as XPASS, a failure does not turn the suite red; the marker goes away
+with the first green GPU run."""
+import ast
+import os
+
+import pytest
+import torch
+
+from tests.parity import three_way
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first GPU run pending (written after the round's GPU budget was spent)")]
+bf16 = torch.bfloat16
+
+
+def test_strided_convolution_as_stride1_plus_pick():
+    """The encoder's downsampling convolutions: stride (2,2,2) / (1,2,2), right/bottom zero pad, causal replicate pad."""
+    import torch.nn.functional as F
+    from easyanimate_b200 import vae_ops
+    g = torch.Generator(device="cuda").manual_seed(1)
+    T, H, W, C = 5, 18, 22, 64
+    x = torch.randn((T, H, W, C), device="cuda", generator=g).to(bf16)
+    w = (torch.randn((C, C, 3, 3, 3), device="cuda", generator=g) * (27 * C) ** -0.5).to(bf16)
+    b = (torch.randn((C,), device="cuda", generator=g) * 0.1).to(bf16)
+    y = vae_ops.conv3d_causal(x, vae_ops.pack_conv_weight(w), b, C)
+    xin = x.float().permute(3, 0, 1, 2)[None]
+    xin = F.pad(F.pad(xin, (0, 1, 0, 1)), (0, 0, 0, 0, 2, 0), mode="replicate")
+    for st in (1, 2):
+        ref = F.conv3d(xin, w.float(), b.float(), stride=(st, 2, 2))[0].permute(1, 2, 3, 0)
+        got = (y[::2] if st == 2 else y)[:, 1::2, 1::2]
+        assert got.shape == ref.shape
+        torch.testing.assert_close(got.float(), ref, rtol=2 ** -7, atol=2e-2)
+
+
+def test_vae_encode_matches_reference_golden():
+    """Against the moments produced by the REFERENCE's AutoencoderKLMagvit.encode / tiled_encode (fp32, CPU)."""
+    from safetensors import safe_open
+    from safetensors.torch import load_file
+    from oracle import vae
+    from easyanimate_b200.autoencoder_magvit import AutoencoderKLMagvit
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vae_ref_encode.safetensors")
+    t = load_file(path)
+    with safe_open(path, framework="pt") as f:
+        meta = f.metadata()
+    boc = list(ast.literal_eval(meta["block_out_channels"]))
+    o32 = vae.init_weights_(vae.OracleAutoencoderKLMagvit(block_out_channels=boc, with_encoder=True), int(meta["seed"]))
+    ob = vae.OracleAutoencoderKLMagvit(block_out_channels=boc, with_encoder=True).to(bf16)
+    ob.load_state_dict({k: v.to(bf16) for k, v in o32.state_dict().items()})
+    ours = AutoencoderKLMagvit(latent_channels=16, cache_mag_vae=True, spatial_group_norm=True, mid_block_attention_type="spatial",
+                               block_out_channels=boc).to(bf16)
+    ours.load_state_dict(ob.state_dict(), strict=True)
+    ours = ours.cuda()
+    x = t["x"].to(bf16)
+    with torch.no_grad():
+        ref = ob.encode_moments(x)
+        post = ours.encode(x.cuda()).latent_dist
+    assert post.parameters.shape == t["moments"].shape and post.mode().shape[1] == 16
+    three_way(post.parameters, ref, t["moments"], name="vae_encode_vs_reference_fixture")
+    # tiled_encode with 32-pixel tiles
+    for m in (ob, ours):
+        m.use_tiling, m.tile_sample_min_size, m.tile_latent_min_size = True, 32, 4
+    with torch.no_grad():
+        ref_t = ob.encode_moments(x)
+        got_t = ours.encode(x.cuda(), return_dict=False)[0].parameters
+    three_way(got_t, ref_t, t["moments_tiled32"], name="vae_tiled_encode_vs_reference_fixture")
+    # run-to-run reproducible
+    with torch.no_grad():
+        assert torch.equal(ours.encode(x.cuda())[0].parameters, got_t)
