@@ -248,7 +248,9 @@ class OracleEncoder(nn.Module):
 
     def forward(self, x):
         assert (x.shape[2] - 1) % 4 == 0, "the reference's chunking needs 1 + 4m frames"
-        x = self.conv_in(x)
+        # (contiguous: PyTorch's CPU bf16 conv3d intermittently returns NaN for a strided tile view with a degenerate
+        #  width - 2 of 150 runs on an [1,3,5,32,8] slice; it changes nothing arithmetically)
+        x = self.conv_in(x.contiguous())
         for down in self.down_blocks:
             x = down(x)
         x = self.mid_block(x)
@@ -298,7 +300,7 @@ class OracleAutoencoderKLMagvit(nn.Module):
         for i in range(0, z.shape[3], overlap_size):
             row = []
             for j in range(0, z.shape[4], overlap_size):
-                tile = z[:, :, :, i:i + tl, j:j + tl]
+                tile = z[:, :, :, i:i + tl, j:j + tl].contiguous()  # (see OracleEncoder.forward)
                 row.append(self.decoder(self.post_quant_conv(tile)))
             rows.append(row)
         result_rows = []
