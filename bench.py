@@ -228,15 +228,30 @@ def main():
     assert args.warmup >= 3 or args.preset == "tiny", "timing rules: at least 3 warm-up steps"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    cfg_group = None
+    cfg_group = sp_group = None
+    single_video = os.environ.get("EA_BENCH_TOPOLOGY", "") == "single_video"
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
         assert world % 2 == 0, "N>1 runs CFG-parallel pairs: N must be even"
-        for g0 in range(0, world, 2):  # every rank must create every group
-            grp = dist.new_group([g0, g0 + 1])
-            if rank in (g0, g0 + 1):
-                cfg_group = grp
+        if single_video and world >= 4:
+            # opt-in (EA_BENCH_TOPOLOGY=single_video): ONE video on all N GPUs = 2 CFG branches x N/2 sequence-parallel
+            # ranks (Ulysses, easyanimate_b200/sequence_parallel.py).  Host logic verified on gloo
+            # (tests/test_dist_sp_cpu.py); not yet validated on GPUs, hence not the default.
+            P = world // 2
+            for b in range(2):  # every rank must create every group
+                grp = dist.new_group(list(range(b * P, (b + 1) * P)))
+                if rank // P == b:
+                    sp_group = grp
+            for r in range(P):
+                grp = dist.new_group([r, r + P])
+                if rank % P == r:
+                    cfg_group = grp
+        else:
+            for g0 in range(0, world, 2):  # every rank must create every group
+                grp = dist.new_group([g0, g0 + 1])
+                if rank in (g0, g0 + 1):
+                    cfg_group = grp
 
     bf16 = torch.bfloat16
     F, h, w = preset["F"], preset["h"], preset["w"]
@@ -250,11 +265,13 @@ def main():
             else:
                 prm.normal_(0.0, 0.02)
     n_params = sum(p.numel() for p in model.parameters())
+    if sp_group is not None:
+        model.set_sequence_parallel_group(sp_group)
     sampler = EasyAnimateSampler(model, guidance_scale=GUIDANCE, cfg_group=cfg_group)
     total_steps = args.warmup + 2 * args.steps + 4
     sampler.set_timesteps(max(total_steps, 30), device="cpu")
     rope = rope_table(h * 8, w * 8, F, device=dev)
-    video_seed = 100 + (rank // 2 if world > 1 else 0)  # one video per CFG pair
+    video_seed = 100 + (0 if sp_group is not None else (rank // 2 if world > 1 else 0))  # one video per CFG pair
     g = torch.Generator(device=dev).manual_seed(video_seed)
     latents = torch.randn((1, 16, F, h, w), device=dev, generator=g).to(bf16)
     embeds = (torch.randn((2, S_TEXT, E_TEXT), device=dev, generator=g) * 10).to(bf16)  # cat(negative, positive)
@@ -308,7 +325,7 @@ def main():
         import torch.distributed as dist
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e = float(t_dev[0]), float(t_dev[1])
-    n_videos = max(1, world // 2)
+    n_videos = 1 if sp_group is not None else max(1, world // 2)
     ms_per_step = ms_total / args.steps
     value = n_videos * args.steps / (ms_total / 1e3)
     e2e_value = n_videos * args.steps / (ms_e2e / 1e3)
@@ -323,7 +340,8 @@ def main():
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
         S = F * (h // 2) * (w // 2) + S_TEXT
         B_attn = 2 if cfg_group is None else 1
-        attn_flops = 4.0 * B_attn * preset["heads"] * S * S * 64
+        heads_attn = preset["heads"] // (world // 2) if sp_group is not None else preset["heads"]  # Ulysses: heads sharded
+        attn_flops = 4.0 * B_attn * heads_attn * S * S * 64
         attn_avg_ms = statistics.mean(attn_ms) if attn_ms else None
         achieved = attn_flops / (attn_avg_ms * 1e-3) / 1e12 if attn_avg_ms else None
         flops_step = 2 * dit_flops_per_forward(**preset)
@@ -331,12 +349,14 @@ def main():
         line = {
             "metric": "denoising-steps/sec @49f·720p bf16 (CFG step = 2 MMDiT forwards)", "value": value, "unit": "steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if sp_group is not None else "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
             "config": {"workload": args.preset, "model": f"MMDiT d={preset['heads'] * 64} heads={preset['heads']} layers={preset['layers']}",
                        "params": n_params, "latent": [1, 16, F, h, w], "video": f"{4 * (F - 1) + 1}f {h * 8}x{w * 8}",
                        "tokens": S, "text_tokens": S_TEXT, "guidance_scale": GUIDANCE, "scheduler": "flow-match Euler shift=1",
                        "parallelism": "single GPU (CFG batch 2)" if world == 1 else
-                       f"{n_videos} video(s) x CFG-parallel pair (1 all_gather of {latents.numel() * 2 / 1e6:.2f} MB per step)",
+                       (f"1 video on {world} GPUs: 2 CFG branches x {world // 2} sequence-parallel ranks (Ulysses)" if sp_group is not None else
+                        f"{n_videos} video(s) x CFG-parallel pair (1 all_gather of {latents.numel() * 2 / 1e6:.2f} MB per step)"),
                        "l2": ("inputs_exceed_L2" if act_bytes > 126e6 else "inputs_fit_L2 (not a timing configuration)") +
                              f" (one activation tensor of a forward is {act_bytes / 1e6:.0f} MB, weights {n_params * 2 / 1e9:.1f} GB)",
                        "tflop_per_step": flops_step / 1e12},
@@ -352,7 +372,7 @@ def main():
                          # this kernel on this shape (profiles/r01_ncu_attn_v6_step_summary.txt: 2.3135 GB at B=2, i.e.
                          # exactly Q+K+V+O once); not re-measured live
                          "traffic": (1.746926e9 + 0.566597e9) * B_attn / 2 if args.preset == "R720_7B" else None,
-                         "traffic_algorithmic": 4.0 * B_attn * preset["heads"] * S * 64 * 2,
+                         "traffic_algorithmic": 4.0 * B_attn * heads_attn * S * 64 * 2,
                          "launches_timed": len(attn_ms), "avg_ms": attn_avg_ms, "flops_per_launch": attn_flops,
                          "share_of_step": (sum(attn_ms) / ms_total) if attn_ms else None},
         }

@@ -120,3 +120,61 @@ def test_sequence_parallel_forward_equals_single_process_forward():
     # every per-token op sees the same rows and attention sees the same keys: identical, not just close
     assert torch.equal(res[0][1], res[1][1])
     assert torch.equal(res[0][1], single)
+
+
+# ---- one video on 4 ranks: 2 CFG branches x 2 sequence-parallel ranks (the 8-GPU single-video topology at small scale) ----
+def _sampler_run(sp_group=None, cfg_group=None):
+    from oracle import dit
+    from tests import cpu_ops
+    from easyanimate_b200.pipeline import EasyAnimateSampler
+    from easyanimate_b200.transformer3d import EasyAnimateTransformer3DModel
+    bf16 = torch.bfloat16
+    ob = dit.init_weights_(dit.OracleTransformer3D(**CFG), 11).to(bf16)
+    m = EasyAnimateTransformer3DModel(**CFG).to(bf16)
+    m.load_state_dict(ob.state_dict(), strict=True)
+    m.set_sequence_parallel_group(sp_group)
+    g = torch.Generator().manual_seed(8)
+    lat = torch.randn(1, 16, 3, 8, 12, generator=g).to(bf16)
+    emb = (torch.randn(2, 9, 128, generator=g) * 3).to(bf16)  # cat(negative, positive)
+    from easyanimate_b200.pipeline import rope_table
+    rope = rope_table(64, 96, 3)
+    s = EasyAnimateSampler(m, guidance_scale=6.0, cfg_group=cfg_group, euler_fn=cpu_ops.cfg_euler_step)
+    s.set_timesteps(3, device="cpu")
+    with torch.no_grad():
+        for i in range(3):
+            lat = s.step(lat, i, emb, rope)
+    return lat.float()
+
+
+def _topology_worker(rank, port, q_out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE="4")
+    dist.init_process_group("gloo", rank=rank, world_size=4)
+    _install_cpu_ops()
+    sp_groups = [dist.new_group([0, 1]), dist.new_group([2, 3])]      # every rank creates every group
+    cfg_pairs = [dist.new_group([0, 2]), dist.new_group([1, 3])]      # rank r (uncond branch) <-> rank r + 2 (text branch)
+    out = _sampler_run(sp_group=sp_groups[rank // 2], cfg_group=cfg_pairs[rank % 2])
+    q_out.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_cfg_pairs_times_sequence_parallel_equals_single_process_sampler():
+    ctx = mp.get_context("spawn")
+    q_out = ctx.Queue()
+    port = 29500 + (os.getpid() % 90)
+    procs = [ctx.Process(target=_topology_worker, args=(r, port, q_out)) for r in range(4)]
+    for p in procs:
+        p.start()
+    res = sorted([q_out.get(timeout=300) for _ in range(4)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    _install_cpu_ops()
+    try:
+        single = _sampler_run()
+    finally:
+        import importlib
+        from easyanimate_b200 import ops
+        importlib.reload(ops)
+    for rank, out in res:
+        assert torch.equal(out, single), rank
