@@ -188,6 +188,24 @@ def rel_l1_distance(cur: torch.Tensor, prev: torch.Tensor) -> float:
     return float((mean_diff / mean_prev).item())
 
 
+def l1_sums(cur: torch.Tensor, prev: torch.Tensor) -> Tuple[float, float]:
+    """(sum |bf16(cur - prev)|, sum |prev|) as the two doubles ea_l1_sums produces: the additive pieces of
+    rel_l1_distance, for callers that combine them across ranks first (sequence parallelism)."""
+    _req(cur, name="cur"); _req(prev, name="prev")
+    assert cur.shape == prev.shape and cur.is_contiguous() and prev.is_contiguous()
+    sums = torch.empty((2,), device=cur.device, dtype=torch.float64)
+    L.check(L.ea_l1_sums(_p(cur), _p(prev), _p(sums), cur.numel(), _stream()), "ea_l1_sums")
+    num, den = (float(x) for x in sums.cpu())
+    return num, den
+
+
+def rel_l1_from_sums(num: float, den: float, n: int) -> float:
+    """The reference's bf16 rounding of each mean and of their ratio (transformer3d.py:113-117) from global sums."""
+    mean_diff = torch.tensor(num / n, dtype=torch.float32).to(bf16)
+    mean_prev = torch.tensor(den / n, dtype=torch.float32).to(bf16)
+    return float((mean_diff / mean_prev).item())
+
+
 def ew_add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, subtract: bool = False) -> torch.Tensor:
     _req(a, name="a"); _req(b, name="b")
     assert a.shape == b.shape and a.is_contiguous() and b.is_contiguous()

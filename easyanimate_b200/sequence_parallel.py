@@ -7,7 +7,8 @@ tokens are few (256) and replicated.  Two exchanges per block, both plain NCCL c
     out    [B, S_v, (H/P)*64]       --all_to_all-->  [B, S_loc, H*64]  (+ all_gather of the text rows)
 
 STATUS: the exchange logic is covered by a world_size-2 gloo test against single-process attention
-(tests/test_dist_cpu.py); the model integration (`EasyAnimateTransformer3DModel.set_sequence_parallel_group`) has NOT run
+(tests/test_dist_sp_cpu.py, which also runs the whole forward, a TeaCache sequence and the 2 CFG branches x 2 ranks sampler
+topology with CPU stand-ins for the kernels); the model integration (`EasyAnimateTransformer3DModel.set_sequence_parallel_group`) has NOT run
 on GPUs yet - tools/test_multigpu.py checks it against the single-GPU forward and is the first thing to run next round.
 The B200-native form of these exchanges (P2P stores from the QKV-GEMM / attention epilogues into the peers' buffers) is
 DESIGN.md section 8, item 3; this NCCL version is the baseline it will be measured against.
@@ -45,6 +46,14 @@ class UlyssesAttention:
         out = torch.empty((self.world * B * S_loc, c), device=x_loc.device, dtype=x_loc.dtype)
         dist.all_gather_into_tensor(out, x_loc.contiguous(), group=self.group)
         return out.view(self.world, B, S_loc, c).permute(1, 0, 2, 3).reshape(B * self.world * S_loc, c).contiguous()
+
+    def all_reduce_sums(self, values) -> list:
+        """Sum a short list of Python floats over the group (TeaCache's rel-L1 pieces)."""
+        t = torch.tensor(list(values), dtype=torch.float64)
+        if dist.get_backend(self.group) == "nccl":
+            t = t.cuda()
+        dist.all_reduce(t, group=self.group)
+        return [float(v) for v in t.cpu()]
 
     # ---- attention with the two exchanges -----------------------------------------------------------------------
     def attention(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, S_t: int):

@@ -383,8 +383,6 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
         sp = self.sequence_parallel
         S_v_full = S_v
         if sp is not None:
-            if self.teacache is not None:
-                raise NotImplementedError("TeaCache with sequence parallelism needs an all-reduce of the rel-L1 sums")
             s0, s1 = sp.local_range(S_v)
             x_v = sp.shard_tokens(x_v, B, S_v)
             if rope is not None:
@@ -403,7 +401,11 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
             if tc.cnt == 0 or tc.cnt == tc.num_steps - 1:
                 tc.accumulated_rel_l1_distance = 0
             else:
-                dist = ops.rel_l1_distance(modulated, tc.previous_modulated_input)
+                if sp is None:
+                    dist = ops.rel_l1_distance(modulated, tc.previous_modulated_input)
+                else:  # the decision must be the same on every rank: combine the additive pieces over the group
+                    num, den = sp.all_reduce_sums(ops.l1_sums(modulated, tc.previous_modulated_input))
+                    dist = ops.rel_l1_from_sums(num, den, modulated.numel() * sp.world)
                 tc.accumulated_rel_l1_distance += tc.rescale_func(dist)
                 if tc.accumulated_rel_l1_distance < tc.rel_l1_thresh:
                     should_calc = False

@@ -134,17 +134,22 @@ def ew_add(a, b, out=None, subtract=False):
     return y
 
 
+def l1_sums(cur, prev):
+    num = (cur.float() - prev.float()).to(bf16).double().abs().sum().item()
+    return num, prev.double().abs().sum().item()
+
+
 def rel_l1_distance(cur, prev):
-    num = (cur.float() - prev.float()).to(bf16).float().abs().mean().to(bf16)
-    den = prev.float().abs().mean().to(bf16)
-    return float((num / den).item())
+    from easyanimate_b200.ops import rel_l1_from_sums
+    num, den = l1_sums(cur, prev)
+    return rel_l1_from_sums(num, den, cur.numel())
 
 
 def install(monkeypatch):
     """Route easyanimate_b200.ops (as seen by transformer3d) to the stand-ins above."""
     from easyanimate_b200 import ops
     for name in ("gemm", "skinny_linear", "layernorm_modulate", "rmsnorm", "timestep_embedding", "patchify", "unpatchify",
-                 "qkv_gemm_ln_rope", "attention", "ew_add", "rel_l1_distance"):
+                 "qkv_gemm_ln_rope", "attention", "ew_add", "rel_l1_distance", "l1_sums"):
         monkeypatch.setattr(ops, name, globals()[name])
 
 

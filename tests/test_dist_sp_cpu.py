@@ -68,11 +68,11 @@ def _install_cpu_ops():
     from easyanimate_b200 import ops
     from tests import cpu_ops
     for name in ("gemm", "skinny_linear", "layernorm_modulate", "rmsnorm", "timestep_embedding", "patchify", "unpatchify",
-                 "qkv_gemm_ln_rope", "attention", "ew_add", "rel_l1_distance"):
+                 "qkv_gemm_ln_rope", "attention", "ew_add", "rel_l1_distance", "l1_sums"):
         setattr(ops, name, getattr(cpu_ops, name))
 
 
-def _forward(sp_group=None):
+def _forward(sp_group=None, teacache=False):
     from oracle import dit
     from easyanimate_b200.transformer3d import EasyAnimateTransformer3DModel
     bf16 = torch.bfloat16
@@ -86,15 +86,25 @@ def _forward(sp_group=None):
     t = torch.tensor([937.0, 421.0]).to(bf16)
     rope = dit.rope_for_video(64, 96, 3)
     with torch.no_grad():
-        return m(lat, t, encoder_hidden_states=enc, image_rotary_emb=rope, return_dict=False)[0]
+        if not teacache:
+            return m(lat, t, encoder_hidden_states=enc, image_rotary_emb=rope, return_dict=False)[0]
+        m.enable_teacache(6, 0.08, coefficients=[1.07862322, -4.19362456, 3.06725828, 0.33161686, 0.02374758])
+        outs = []
+        for i in range(6):
+            x, tt = (lat.float() * (1.0 - 0.01 * i)).to(bf16), torch.tensor([900.0 - 30 * i] * 2).to(bf16)
+            outs.append(m(x, tt, encoder_hidden_states=enc, image_rotary_emb=rope, return_dict=False)[0])
+        assert m.teacache.skipped >= 1
+        return torch.stack(outs)
 
 
 def _model_worker(rank, port, q_out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE="2")
     dist.init_process_group("gloo", rank=rank, world_size=2)
     _install_cpu_ops()
-    out = _forward(dist.new_group([0, 1]))
-    q_out.put((rank, out.float()))
+    grp = dist.new_group([0, 1])
+    out = _forward(grp)
+    out_tc = _forward(grp, teacache=True)
+    q_out.put((rank, out.float(), out_tc.float()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -113,6 +123,7 @@ def test_sequence_parallel_forward_equals_single_process_forward():
     _install_cpu_ops()
     try:
         single = _forward(None).float()
+        single_tc = _forward(None, teacache=True).float()
     finally:
         import importlib
         from easyanimate_b200 import ops
@@ -120,6 +131,9 @@ def test_sequence_parallel_forward_equals_single_process_forward():
     # every per-token op sees the same rows and attention sees the same keys: identical, not just close
     assert torch.equal(res[0][1], res[1][1])
     assert torch.equal(res[0][1], single)
+    # TeaCache under sequence parallelism: the rel-L1 pieces are summed over the group, so every rank takes the same
+    # skip decisions as the single-process run (6 calls, at least one served from the cached residual)
+    assert torch.equal(res[0][2], res[1][2]) and torch.equal(res[0][2], single_tc)
 
 
 # ---- one video on 4 ranks: 2 CFG branches x 2 sequence-parallel ranks (the 8-GPU single-video topology at small scale) ----
