@@ -326,6 +326,7 @@ class AutoencoderKLMagvit(nn.Module, ConfigMixinLite):
         self.tile_latent_min_size = int(self.tile_sample_min_size / (2 ** (len(ch_mult) - 1)))
         self.scaling_factor = scaling_factor
         self.tile_parallel_group = None  # torch.distributed group for tile-parallel tiled_decode (one all-gather)
+        self._latent_in_scale = 1.0      # decode_scaled() folds decode_latents' 1/scaling_factor into the first kernel
 
     def set_tile_parallel_group(self, group):
         """Shard the reference's tiled_decode tiles over the ranks of `group` (every rank must call decode with the
@@ -336,7 +337,7 @@ class AutoencoderKLMagvit(nn.Module, ConfigMixinLite):
     def _decode_one(self, z: torch.Tensor) -> torch.Tensor:
         """z [C,T,h,w] planar -> [1,3,T',8h,8w]: post_quant_conv + Decoder (autoencoder_magvit.py:281-282)."""
         pq = self.post_quant_conv
-        x = vae_ops.prepare_latents(z, pq.weight, pq.bias, 64)
+        x = vae_ops.prepare_latents(z, pq.weight, pq.bias, 64, in_scale=self._latent_in_scale)
         return self.decoder.run(x).unsqueeze(0)
 
     def _tiled_decode_one(self, z: torch.Tensor) -> torch.Tensor:
@@ -421,6 +422,28 @@ class AutoencoderKLMagvit(nn.Module, ConfigMixinLite):
         if not return_dict:
             return (decoded,)
         return DecoderOutput(sample=decoded)
+
+    @torch.no_grad()
+    def decode_scaled(self, latents: torch.Tensor, out: Optional[torch.Tensor] = None, dtype=torch.float32,
+                      to_host: bool = False) -> torch.Tensor:
+        """`EasyAnimatePipeline.decode_latents` (pipeline_easyanimate.py:722-742) as ONE call: `1 / scaling_factor *
+        latents` is folded into the latent-preparation kernel (one bf16 rounding, like the reference's tensor op), the decode
+        runs as in decode(), and the tail clamp(-1,1) -> /2+0.5 -> clamp(0,1) -> float32 (or uint8 = trunc(255*v), what
+        utils.py:57 makes of the frames) is ONE kernel whose destination is `out`: a CUDA tensor, or with to_host=True a
+        pinned host tensor the kernel writes over PCIe directly (no bf16 staging copy, no host-side .float()).  The call
+        returns after the stream has been synchronised when the destination is on the host."""
+        self._latent_in_scale = 1.0 / float(self.config.scaling_factor)
+        try:
+            video = self._decode(latents)
+        finally:
+            self._latent_in_scale = 1.0
+        if out is None:
+            out = (torch.empty(video.shape, dtype=dtype, pin_memory=True) if to_host
+                   else torch.empty(video.shape, dtype=dtype, device=video.device))
+        vae_ops.frames_out(video.contiguous(), out)
+        if not out.is_cuda:
+            torch.cuda.current_stream(video.device).synchronize()
+        return out
 
     # ---- encode (I2V / inpaint conditioning prep) ---------------------------------------------------------------
     def _encode_one(self, x: torch.Tensor) -> torch.Tensor:

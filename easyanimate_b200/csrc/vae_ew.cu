@@ -13,7 +13,7 @@ extern void count_launch();
 // autoencoder_magvit.py:281 post_quant_conv (1x1x1 Conv3d) fused with the NCTHW -> THWC transposition.
 __global__ void vae_prepare_latents_kernel(const bf16* __restrict__ z, const bf16* __restrict__ w,
                                            const bf16* __restrict__ bias, bf16* __restrict__ y, int C, int Cpad,
-                                           int64_t thw, int64_t z_c_stride) {
+                                           int64_t thw, int64_t z_c_stride, float in_scale) {
   extern __shared__ float sw[];  // [C*C] weights + [C] bias
   for (int i = threadIdx.x; i < C * C; i += blockDim.x) sw[i] = __bfloat162float(w[i]);
   for (int i = threadIdx.x; i < C; i += blockDim.x) sw[C * C + i] = __bfloat162float(bias[i]);
@@ -21,7 +21,9 @@ __global__ void vae_prepare_latents_kernel(const bf16* __restrict__ z, const bf1
   const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= thw) return;
   float in[32];
-  for (int c = 0; c < C; ++c) in[c] = __bfloat162float(z[c * z_c_stride + pix]);
+  // in_scale: decode_latents' `1 / scaling_factor * latents` (pipeline_easyanimate.py:724), a bf16 tensor op of its own in
+  // the reference, hence one bf16 rounding before the 1x1x1 convolution (exact when in_scale == 1)
+  for (int c = 0; c < C; ++c) in[c] = bf16_round(__bfloat162float(z[c * z_c_stride + pix]) * in_scale);
   bf16* o = y + pix * Cpad;
   for (int co = 0; co < Cpad; co += 2) {
     float a0 = 0.f, a1 = 0.f;
@@ -246,19 +248,85 @@ __global__ void corner_blend_kernel(const bf16* __restrict__ src, bf16* __restri
   *dp = __float2bfloat16_rn(wgt * s + (1.0f - wgt) * d);
 }
 
+// decode_latents' tail (pipeline_easyanimate.py:729,738-740): clamp(-1,1) -> /2 + 0.5 (two bf16 ops) -> clamp(0,1) ->
+// float32 (what `.cpu().float().numpy()` yields) or uint8 = trunc(255 * v) (utils.py:57 `(x * 255).numpy().astype(np.uint8)`).
+// `out` may be device memory or device-mapped pinned host memory: 8 elements per thread, 32 B (16 B) contiguous stores.
+template <typename OutT>
+__global__ void frames_out_kernel(const bf16* __restrict__ x, OutT* __restrict__ out, int64_t n) {
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i0 >= n) return;
+  float v[8];
+  if (i0 + 8 <= n) {
+    const uint4 u = *reinterpret_cast<const uint4*>(x + i0);
+    const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16x2(uw[k]);
+      v[2 * k] = f.x;
+      v[2 * k + 1] = f.y;
+    }
+  } else {
+    for (int k = 0; k < 8; ++k) v[k] = i0 + k < n ? __bfloat162float(x[i0 + k]) : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float a = fminf(fmaxf(v[k], -1.0f), 1.0f);   // video.clamp(-1, 1)      (NaN propagates like torch.clamp)
+    a = v[k] != v[k] ? v[k] : a;
+    a = bf16_round(bf16_round(a * 0.5f) + 0.5f);  // video / 2 + 0.5        (bf16 tensor ops)
+    const float c = fminf(fmaxf(a, 0.0f), 1.0f);  // .clamp(0, 1)
+    v[k] = a != a ? a : c;
+  }
+  if constexpr (sizeof(OutT) == 4) {
+    if (i0 + 8 <= n) {
+      *reinterpret_cast<float4*>(out + i0) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(out + i0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      for (int k = 0; k < 8 && i0 + k < n; ++k) out[i0 + k] = (OutT)v[k];
+    }
+  } else {
+    uint8_t b[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) b[k] = (uint8_t)(int)(v[k] * 255.0f);
+    if (i0 + 8 <= n) {
+      uint2 w;
+      w.x = b[0] | (b[1] << 8) | (b[2] << 16) | ((uint32_t)b[3] << 24);
+      w.y = b[4] | (b[5] << 8) | (b[6] << 16) | ((uint32_t)b[7] << 24);
+      *reinterpret_cast<uint2*>(out + i0) = w;
+    } else {
+      for (int k = 0; k < 8 && i0 + k < n; ++k) out[i0 + k] = (OutT)b[k];
+    }
+  }
+}
+
 }  // namespace ea
 
 using namespace ea;
 
+extern "C" int ea_frames_out(const void* x, void* out, int64_t n, int32_t out_kind, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  EA_REQUIRE(x && out && n > 0, "ea_frames_out: bad arguments");
+  EA_REQUIRE(out_kind == EA_FRAMES_F32 || out_kind == EA_FRAMES_U8, "ea_frames_out: out_kind must be EA_FRAMES_F32 or EA_FRAMES_U8");
+  EA_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+             "ea_frames_out: pointers must be 16-byte aligned");
+  const int64_t threads = (n + 7) / 8;
+  const unsigned blocks = (unsigned)((threads + 255) / 256);
+  if (out_kind == EA_FRAMES_F32)
+    frames_out_kernel<float><<<blocks, 256, 0, stream>>>((const bf16*)x, (float*)out, n);
+  else
+    frames_out_kernel<uint8_t><<<blocks, 256, 0, stream>>>((const bf16*)x, (uint8_t*)out, n);
+  count_launch();
+  return check_launch("frames_out_kernel");
+}
+
 extern "C" int ea_vae_prepare_latents(const void* z, const void* w, const void* bias, void* y, int64_t C, int64_t Cpad,
-                                      int64_t T, int64_t H, int64_t W, void* stream_) {
+                                      int64_t T, int64_t H, int64_t W, float in_scale, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   EA_REQUIRE(z && w && bias && y, "ea_vae_prepare_latents: null pointer");
   EA_REQUIRE(C > 0 && C <= 32 && Cpad >= C && Cpad % 8 == 0, "ea_vae_prepare_latents: need C <= 32, Cpad % 8 == 0");
   const int64_t thw = T * H * W;
   const size_t smem = (size_t)(C * C + C) * sizeof(float);
   vae_prepare_latents_kernel<<<(unsigned)((thw + 127) / 128), 128, smem, stream>>>(
-      (const bf16*)z, (const bf16*)w, (const bf16*)bias, (bf16*)y, (int)C, (int)Cpad, thw, thw);
+      (const bf16*)z, (const bf16*)w, (const bf16*)bias, (bf16*)y, (int)C, (int)Cpad, thw, thw, in_scale);
   count_launch();
   return check_launch("vae_prepare_latents_kernel");
 }

@@ -87,6 +87,8 @@ class EasyAnimateSampler:
             import torch.distributed as dist
             assert dist.get_world_size(cfg_group) == 2, "CFG-parallel needs a group of exactly 2 ranks"
             self._cfg_rank = dist.get_rank(cfg_group)
+            if hasattr(transformer, "set_cfg_parallel_group"):
+                transformer.set_cfg_parallel_group(cfg_group)  # TeaCache decisions from the joint batch of 2
 
     def set_timesteps(self, num_inference_steps: int, device=None):
         self.scheduler.set_timesteps(num_inference_steps, device=device, mu=1.0)  # pipeline_easyanimate.py:972
@@ -94,7 +96,9 @@ class EasyAnimateSampler:
 
     # -- one scheduler step ------------------------------------------------------------------------------------
     def step(self, latents: torch.Tensor, i: int, embeds: torch.Tensor, rope, inpaint_latents=None) -> torch.Tensor:
-        """latents [B,C,F,h,w]; embeds [2B,S_t,E] = cat(negative, positive) when CFG is on (pipeline_easyanimate.py:1052-1056)."""
+        """latents [B,C,F,h,w]; embeds [2B,S_t,E] = cat(negative, positive) when CFG is on (pipeline_easyanimate.py:1052-1056).
+        inpaint_latents: [B,...] (the same conditioning for both branches, what pipeline_easyanimate_inpaint.py:1496-1511
+        builds with cat([x] * 2)) or [2B,...] = cat(unconditional-branch, text-branch) conditioning."""
         t = self.scheduler.timesteps[i]
         sigma, sigma_next = self.scheduler.sigma_pair(i)
         B = latents.shape[0]
@@ -105,7 +109,9 @@ class EasyAnimateSampler:
             return self._euler(pred, latents, 1.0, sigma, sigma_next, use_cfg=False)
         if self.cfg_group is None:
             latent_in = torch.cat([latents] * 2)
-            inp = None if inpaint_latents is None else torch.cat([inpaint_latents] * 2)
+            inp = inpaint_latents
+            if inp is not None and inp.shape[0] == B:
+                inp = torch.cat([inp] * 2)
             t_expand = t.reshape(1).expand(2 * B).to(device=latents.device, dtype=bf16)
             pred = self.transformer(latent_in, t_expand, encoder_hidden_states=embeds, image_rotary_emb=rope,
                                     inpaint_latents=inp, return_dict=False)[0]
@@ -113,8 +119,11 @@ class EasyAnimateSampler:
             import torch.distributed as dist
             r = self._cfg_rank  # rank 0: unconditional branch, rank 1: text-conditioned branch
             t_expand = t.reshape(1).expand(B).to(device=latents.device, dtype=bf16)
+            inp = inpaint_latents
+            if inp is not None and inp.shape[0] == 2 * B:
+                inp = inp[r * B:(r + 1) * B].contiguous()
             mine = self.transformer(latents, t_expand, encoder_hidden_states=embeds[r * B:(r + 1) * B].contiguous(),
-                                    image_rotary_emb=rope, inpaint_latents=inpaint_latents, return_dict=False)[0]
+                                    image_rotary_emb=rope, inpaint_latents=inp, return_dict=False)[0]
             pred = torch.empty((2 * B,) + tuple(mine.shape[1:]), device=mine.device, dtype=mine.dtype)
             dist.all_gather_into_tensor(pred, mine.contiguous(), group=self.cfg_group)
         return self._euler(pred, latents, self.guidance_scale, sigma, sigma_next, use_cfg=True)
@@ -149,8 +158,10 @@ class EasyAnimateSampler:
         return latents
 
     @torch.no_grad()
-    def decode_latents(self, latents: torch.Tensor) -> torch.Tensor:
-        """pipeline_easyanimate.py:722-742 up to the device tensor: /scaling_factor -> vae.decode -> clamp -> [0,1]."""
-        video = self.vae.decode((1 / self.vae.config.scaling_factor * latents).to(bf16))[0]
-        video = video.clamp(-1, 1)
-        return (video / 2 + 0.5).clamp(0, 1)
+    def decode_latents(self, latents: torch.Tensor, out: Optional[torch.Tensor] = None, dtype=torch.float32,
+                       to_host: bool = True) -> torch.Tensor:
+        """pipeline_easyanimate.py:722-742: /scaling_factor -> vae.decode -> clamp(-1,1) -> /2+.5 -> clamp(0,1) ->
+        `.cpu().float()`: returns the [B,3,T,H,W] float32 frames in (pinned) HOST memory by default - `torch.from_numpy` /
+        `.numpy()` views of it are what the reference pipeline hands back as `.frames` (:1139-1149).  No torch arithmetic:
+        the scale rides in the latent-preparation kernel, the tail is `ea_frames_out` (AutoencoderKLMagvit.decode_scaled)."""
+        return self.vae.decode_scaled(latents.to(bf16), out=out, dtype=dtype, to_host=to_host)

@@ -1,5 +1,7 @@
-"""Ulysses sequence parallelism for ONE video across the ranks of a group (the reference's xfuser mode,
-easyanimate/dist/ + predict_t2v.py:56-60 `ulysses_degree`): every rank owns a contiguous slice of the video tokens for the
+"""Ulysses sequence parallelism for ONE video across the ranks of a group.  The reference has no multi-GPU inference code at
+this commit (no xfuser / ulysses / ring); joint text+video attention (processor.py:287-289) makes a
+per-block exchange unavoidable once one video spans more than the two CFG branches, and this module
+is this framework's own design for it: every rank owns a contiguous slice of the video tokens for the
 per-token work (AdaLN, projections, feed-forward) and, inside attention, all tokens of a slice of the HEADS.  The text
 tokens are few (256) and replicated.  Two exchanges per block, both plain NCCL collectives here:
 
@@ -19,6 +21,19 @@ from typing import Callable, Optional, Tuple
 
 import torch
 import torch.distributed as dist
+
+
+def group_size(group) -> int:
+    return dist.get_world_size(group)
+
+
+def all_reduce_floats(values, group) -> list:
+    """Sum a short list of Python floats over `group` (TeaCache's rel-L1 pieces); fp64 on the wire."""
+    t = torch.tensor(list(values), dtype=torch.float64)
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t, group=group)
+    return [float(v) for v in t.cpu()]
 
 
 class UlyssesAttention:
@@ -48,12 +63,7 @@ class UlyssesAttention:
         return out.view(self.world, B, S_loc, c).permute(1, 0, 2, 3).reshape(B * self.world * S_loc, c).contiguous()
 
     def all_reduce_sums(self, values) -> list:
-        """Sum a short list of Python floats over the group (TeaCache's rel-L1 pieces)."""
-        t = torch.tensor(list(values), dtype=torch.float64)
-        if dist.get_backend(self.group) == "nccl":
-            t = t.cuda()
-        dist.all_reduce(t, group=self.group)
-        return [float(v) for v in t.cpu()]
+        return all_reduce_floats(values, self.group)
 
     # ---- attention with the two exchanges -----------------------------------------------------------------------
     def attention(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, S_t: int):

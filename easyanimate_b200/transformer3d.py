@@ -278,6 +278,7 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
         self.proj_out = nn.Linear(d, patch_size * patch_size * out_channels)
         self.teacache = None
         self.sequence_parallel = None  # UlyssesAttention, see set_sequence_parallel_group
+        self.cfg_parallel_group = None  # 2-rank group holding the other CFG branch, see set_cfg_parallel_group
         self.gradient_checkpointing = False
         self._proj_w_cache: Optional[tuple] = None
 
@@ -288,12 +289,20 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
         self.teacache = TeaCache(list(coefficients), num_steps, rel_l1_thresh=rel_l1_thresh)
 
     def set_sequence_parallel_group(self, group):
-        """Ulysses sequence parallelism over the ranks of `group` for ONE video (the reference's xfuser `ulysses_degree`,
-        predict_t2v.py:56-60): every rank calls forward with the same inputs and gets the full output; video tokens and
-        attention heads must divide by the group size.  None restores single-GPU execution.  See sequence_parallel.py
-        for what has and has not been validated."""
+        """Ulysses sequence parallelism over the ranks of `group` for ONE video.  The reference has NO multi-GPU inference
+        path at this commit; this is this framework's own answer to the per-block exchange joint
+        attention needs (processor.py:287-289).  Every rank calls forward with the same inputs and
+        gets the full output; video tokens and attention heads must divide by the group size.  None restores
+        single-GPU execution."""
         from .sequence_parallel import UlyssesAttention
         self.sequence_parallel = None if group is None else UlyssesAttention(group)
+
+    def set_cfg_parallel_group(self, group):
+        """CFG-parallel execution (EasyAnimateSampler(cfg_group=...)): this module sees ONE branch of the reference's
+        batch of 2 (pipeline_easyanimate.py:1074).  The only place where the branches interact inside the transformer is
+        TeaCache, whose skip decision comes from the rel-L1 MEAN over the joint batch (transformer3d.py:1563-1586): the
+        additive pieces are summed over `group` so that both ranks take the reference's decision."""
+        self.cfg_parallel_group = group
 
     def _set_gradient_checkpointing(self, module, value=False):
         self.gradient_checkpointing = value
@@ -401,11 +410,19 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
             if tc.cnt == 0 or tc.cnt == tc.num_steps - 1:
                 tc.accumulated_rel_l1_distance = 0
             else:
-                if sp is None:
+                groups = [g for g in ((sp.group if sp is not None else None), self.cfg_parallel_group) if g is not None]
+                if not groups:
                     dist = ops.rel_l1_distance(modulated, tc.previous_modulated_input)
-                else:  # the decision must be the same on every rank: combine the additive pieces over the group
-                    num, den = sp.all_reduce_sums(ops.l1_sums(modulated, tc.previous_modulated_input))
-                    dist = ops.rel_l1_from_sums(num, den, modulated.numel() * sp.world)
+                else:
+                    # the decision must be the reference's (one per step, from the means over ALL tokens of BOTH CFG
+                    # branches) and the same on every rank: combine the additive pieces over the ranks of this video
+                    from .sequence_parallel import all_reduce_floats, group_size
+                    num, den = ops.l1_sums(modulated, tc.previous_modulated_input)
+                    n = modulated.numel()
+                    for g in groups:
+                        num, den = all_reduce_floats((num, den), g)
+                        n *= group_size(g)
+                    dist = ops.rel_l1_from_sums(num, den, n)
                 tc.accumulated_rel_l1_distance += tc.rescale_func(dist)
                 if tc.accumulated_rel_l1_distance < tc.rel_l1_thresh:
                     should_calc = False

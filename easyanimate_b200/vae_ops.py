@@ -42,15 +42,30 @@ def pack_conv_weight(w: torch.Tensor, cin_pad: int = 0, cout_pad: int = 0) -> to
     return wp.reshape(cout_pad, 27 * cin_pad).contiguous()
 
 
-def prepare_latents(z: torch.Tensor, w: torch.Tensor, b: torch.Tensor, cpad: int = 64) -> torch.Tensor:
-    """z [C,T,H,W] planar -> post_quant_conv -> [T,H,W,cpad] channels-last."""
+def prepare_latents(z: torch.Tensor, w: torch.Tensor, b: torch.Tensor, cpad: int = 64, in_scale: float = 1.0) -> torch.Tensor:
+    """z [C,T,H,W] planar -> bf16(in_scale * z) -> post_quant_conv -> [T,H,W,cpad] channels-last."""
     _req(z, name="z")
     Cc, T, H, W = z.shape
     z = z.contiguous()
     y = torch.empty((T, H, W, cpad), device=z.device, dtype=bf16)
     L.check(L.ea_vae_prepare_latents(_p(z), _p(w.reshape(Cc, Cc).contiguous()), _p(b), _p(y), Cc, cpad, T, H, W,
-                                     _stream()), "ea_vae_prepare_latents")
+                                     float(in_scale), _stream()), "ea_vae_prepare_latents")
     return y
+
+
+def frames_out(video: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """decode_latents' tail (pipeline_easyanimate.py:729,738-741) in one pass: video bf16 (any shape, contiguous) ->
+    out = clamp(clamp(video,-1,1)/2+0.5, 0, 1) as float32 or uint8 (trunc(255*v)).  `out` is a CUDA tensor or a PINNED host
+    tensor (the kernel then stores straight into host memory over PCIe; the caller synchronises the stream before reading)."""
+    _req(video, name="video")
+    assert video.is_contiguous() and out.is_contiguous() and out.numel() == video.numel()
+    if out.dtype not in (torch.float32, torch.uint8):
+        raise L.EaError(f"frames_out writes float32 or uint8, got {out.dtype}")
+    if not out.is_cuda and not out.is_pinned():
+        raise L.EaError("frames_out: a host destination must be pinned memory (torch.empty(..., pin_memory=True))")
+    kind = L.FRAMES_F32 if out.dtype == torch.float32 else L.FRAMES_U8
+    L.check(L.ea_frames_out(_p(video), out.data_ptr(), video.numel(), kind, _stream()), "ea_frames_out")
+    return out
 
 
 def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, silu: bool) -> torch.Tensor:

@@ -228,10 +228,18 @@ typedef struct {
 
 int ea_conv3d_causal(const ea_conv3d_args* args, void* stream);
 
-/* post_quant_conv (1x1x1, autoencoder_magvit.py:182,281) fused with NCTHW->THWC: z [C,T,H,W] planar ->
- * y [T,H,W,Cpad] (channels >= C zero). C <= 32. */
+/* post_quant_conv (1x1x1, autoencoder_magvit.py:182,281) fused with NCTHW->THWC and with decode_latents'
+ * `1 / scaling_factor * latents` (pipeline_easyanimate.py:724; in_scale = 1 leaves z untouched): z [C,T,H,W] planar ->
+ * y [T,H,W,Cpad] = bf16(W * bf16(in_scale * z) + bias) (channels >= C zero). C <= 32. */
 int ea_vae_prepare_latents(const void* z, const void* w, const void* bias, void* y, int64_t C, int64_t Cpad, int64_t T,
-                           int64_t H, int64_t W, void* stream);
+                           int64_t H, int64_t W, float in_scale, void* stream);
+
+/* decode_latents' tail (pipeline_easyanimate.py:729,738-741): out = clamp(bf16(bf16(clamp(x,-1,1) / 2) + 0.5), 0, 1) over
+ * n bf16 elements, written as float32 (what `.cpu().float().numpy()` returns) or as uint8 = trunc(255 * v)
+ * (utils.py:57).  `out` is a device pointer OR a device-mapped pinned HOST pointer (cudaHostAlloc / torch pin_memory under
+ * UVA): the frames then go straight to host memory without a device staging copy.  Both pointers 16-byte aligned. */
+enum { EA_FRAMES_F32 = 0, EA_FRAMES_U8 = 1 };
+int ea_frames_out(const void* x, void* out, int64_t n, int32_t out_kind, void* stream);
 
 /* Per-frame GroupNorm (common.py:301-319 with set_3dgroupnorm; omnigen_enc_dec.py:603-609):
  * stats[frames,groups,2] = (mean, rstd) fp32; workspace = ea_groupnorm_workspace() bytes of scratch. */

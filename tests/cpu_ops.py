@@ -172,9 +172,10 @@ def conv3d_causal(x, w_packed, bias, cout, *, residual=None, dup_frames=False, o
     return y.contiguous() if out_planar else y.permute(1, 2, 3, 0).contiguous()
 
 
-def prepare_latents(z, w, b, cpad=64):
+def prepare_latents(z, w, b, cpad=64, in_scale=1.0):
     Cc, T, H, W = z.shape
-    y = _r(torch.einsum("oc,cthw->othw", w.float().reshape(Cc, Cc), z.float()) + b.float()[:, None, None, None])
+    zs = _r(z.float() * torch.tensor(in_scale, dtype=torch.float32))
+    y = _r(torch.einsum("oc,cthw->othw", w.float().reshape(Cc, Cc), zs) + b.float()[:, None, None, None])
     out = torch.zeros((T, H, W, cpad), dtype=bf16)
     out[..., :Cc] = y.permute(1, 2, 3, 0)
     return out
@@ -229,10 +230,17 @@ def corner_blend(src, dst):
     dst[..., -Hc:, -Wc:] = (wgt * src.float() + (1 - wgt) * area).to(bf16)
 
 
+def frames_out(video, out):
+    """include/ea_b200.h ea_frames_out: the reference's op sequence on a bf16 tensor (pipeline_easyanimate.py:729,738-741)."""
+    v = (video.clamp(-1, 1) / 2 + 0.5).clamp(0, 1).float()
+    out.copy_(v if out.dtype == torch.float32 else (v * 255).to(torch.uint8))
+    return out
+
+
 def install_vae(monkeypatch):
     from easyanimate_b200 import ops, vae_ops
     for name in ("conv3d_causal", "prepare_latents", "groupnorm", "upsample2x", "spatial_attention", "tile_blend", "copy2d",
-                 "corner_blend"):
+                 "corner_blend", "frames_out"):
         monkeypatch.setattr(vae_ops, name, globals()[name])
     monkeypatch.setattr(ops, "gemm", gemm)
 

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/ea_b200.h but not exported"
     lib.ea_abi_version.restype = ctypes.c_int
-    assert lib.ea_abi_version() == 1
+    assert lib.ea_abi_version() == 2
     lib.ea_last_error.restype = ctypes.c_char_p
     assert isinstance(lib.ea_last_error(), bytes)
 

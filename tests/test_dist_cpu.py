@@ -96,3 +96,79 @@ def test_rope_table_mirror_matches_oracle():
     for (hh, ww, f) in ((720, 1280, 13), (512, 512, 13), (64, 64, 1), (384, 672, 7)):
         a, b = rope_table(hh, ww, f), dit.rope_for_video(hh, ww, f)
         assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+# ---- TeaCache under CFG-parallel: the skip decision is the reference's joint-batch decision on both ranks ----
+_TC_CFG = dict(num_attention_heads=2, attention_head_dim=64, in_channels=33, out_channels=16, patch_size=2, num_layers=2,
+               time_embed_dim=64, add_norm_text_encoder=True, text_embed_dim=128, text_embed_dim_t5=None)
+_TC_COEFFS = [1.07862322, -4.19362456, 3.06725828, 0.33161686, 0.02374758]
+
+
+def _install_cpu_ops():
+    from easyanimate_b200 import ops
+    from tests import cpu_ops
+    for name in ("gemm", "skinny_linear", "layernorm_modulate", "rmsnorm", "timestep_embedding", "patchify", "unpatchify",
+                 "qkv_gemm_ln_rope", "attention", "ew_add", "rel_l1_distance", "l1_sums"):
+        setattr(ops, name, getattr(cpu_ops, name))
+
+
+def _teacache_sampler_run(cfg_group=None, steps=8, thresh=0.15):
+    """8 sampler steps with TeaCache on; returns (latents, skipped-forward count)."""
+    from oracle import dit
+    from tests import cpu_ops
+    from easyanimate_b200.pipeline import EasyAnimateSampler, rope_table
+    from easyanimate_b200.transformer3d import EasyAnimateTransformer3DModel
+    ob = dit.init_weights_(dit.OracleTransformer3D(**_TC_CFG), 11).to(bf16)
+    m = EasyAnimateTransformer3DModel(**_TC_CFG).to(bf16)
+    m.load_state_dict(ob.state_dict(), strict=True)
+    m.enable_teacache(steps, thresh, coefficients=_TC_COEFFS)
+    g = torch.Generator().manual_seed(8)
+    lat = torch.randn(1, 16, 3, 8, 12, generator=g).to(bf16)
+    emb = torch.cat([torch.randn(1, 9, 128, generator=g) * 0.2, torch.randn(1, 9, 128, generator=g) * 8.0]).to(bf16)
+    # TeaCache looks at block 0's modulated VIDEO input, which the text does not reach: the branches differ there only through
+    # their conditioning latents.  Give the two branches very different ones, so that per-rank decisions would differ from
+    # the joint-batch decision (with identical conditioning the per-branch means equal the joint mean and nothing is tested).
+    inp = torch.cat([torch.zeros(1, 17, 3, 8, 12), torch.randn(1, 17, 3, 8, 12, generator=g) * 4.0]).to(bf16)
+    rope = rope_table(64, 96, 3)
+    s = EasyAnimateSampler(m, guidance_scale=6.0, cfg_group=cfg_group, euler_fn=cpu_ops.cfg_euler_step)
+    s.set_timesteps(steps, device="cpu")
+    with torch.no_grad():
+        for i in range(steps):
+            lat = s.step(lat, i, emb, rope, inpaint_latents=inp)
+    return lat.float(), m.teacache.skipped
+
+
+def _teacache_worker(rank, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE="2")
+    dist.init_process_group("gloo", rank=rank, world_size=2)
+    _install_cpu_ops()
+    out, skipped = _teacache_sampler_run(dist.new_group([0, 1]))
+    q.put((rank, out, skipped))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_teacache_with_cfg_parallel_takes_the_joint_batch_decision():
+    """with cfg_group each rank sees one branch (B=1); the reference decides skip/compute once per step
+    from the rel-L1 means over the batch of 2 (transformer3d.py:1563-1586).  The (num, den) sums are all-reduced over the
+    CFG pair, so both ranks skip exactly where the single-process batch-of-2 run skips and the latents agree bit for bit."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() % 90)
+    procs = [ctx.Process(target=_teacache_worker, args=(r, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict((r, (o, s)) for r, o, s in (q.get(timeout=180) for _ in range(2)))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    _install_cpu_ops()
+    try:
+        single, skipped = _teacache_sampler_run(None)
+    finally:
+        import importlib
+        from easyanimate_b200 import ops
+        importlib.reload(ops)
+    assert skipped >= 1, "the test must exercise the cached path"
+    assert res[0][1] == res[1][1] == skipped, (res[0][1], res[1][1], skipped)
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][0], single)

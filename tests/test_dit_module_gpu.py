@@ -8,7 +8,7 @@ pytestmark = pytest.mark.gpu
 bf16 = torch.bfloat16
 
 
-def _build(cfg, seed=1234):
+def _build(cfg, seed=1234, device="cuda"):
     from oracle import dit
     from easyanimate_b200.transformer3d import EasyAnimateTransformer3DModel
     o32 = dit.init_weights_(dit.OracleTransformer3D(**cfg), seed)
@@ -17,7 +17,8 @@ def _build(cfg, seed=1234):
     o32.load_state_dict({k: v.float() for k, v in ob.state_dict().items()})  # truth uses the bf16-rounded weights
     ours = EasyAnimateTransformer3DModel(**cfg).to(bf16)
     missing, unexpected = ours.load_state_dict(ob.state_dict(), strict=True)
-    return o32, ob, ours.cuda()
+    assert not missing and not unexpected
+    return o32, ob, ours.to(device)
 
 
 def _inputs(B, C, F, H, W, S_t, E, seed=0):
@@ -57,22 +58,27 @@ def test_transformer_forward_matches_oracle(name, cfg, shape):
     three_way(got, ref, truth, name=name)
 
 
-@pytest.mark.parametrize("name", ["dit_ref_t2v", "dit_ref_i2v_inpaint", "dit_ref_3heads_3layers"])
-def test_transformer_forward_matches_reference_golden(name):
-    """Against outputs of the REFERENCE's own EasyAnimateTransformer3DModel (fp32, minted by tests/golden/make_golden.py
-    in the authoring container): our bf16 kernels are as close to it as the bf16 oracle is."""
+def prelude_reference_golden(name, device="cuda"):
+    """Fixture + oracle pair + product module of the reference-golden test (no GPU needed for device='cpu')."""
     import ast
     import os
     from safetensors import safe_open
     from safetensors.torch import load_file
-    from oracle import dit
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"{name}.safetensors")
     t = load_file(path)
     with safe_open(path, framework="pt") as f:
         meta = f.metadata()
     cfg = ast.literal_eval(meta["config"])
-    B, F, H, W, St = ast.literal_eval(meta["shape"])
-    o32, ob, ours = _build(cfg, seed=int(meta["seed"]))
+    shape = ast.literal_eval(meta["shape"])
+    return t, cfg, shape, _build(cfg, seed=int(meta["seed"]), device=device)
+
+
+@pytest.mark.parametrize("name", ["dit_ref_t2v", "dit_ref_i2v_inpaint", "dit_ref_3heads_3layers"])
+def test_transformer_forward_matches_reference_golden(name):
+    """Against outputs of the REFERENCE's own EasyAnimateTransformer3DModel (fp32, minted by tests/golden/make_golden.py
+    in the authoring container): our bf16 kernels are as close to it as the bf16 oracle is."""
+    from oracle import dit
+    t, cfg, (B, F, H, W, St), (o32, ob, ours) = prelude_reference_golden(name)
     rope = dit.rope_for_video(H * 8, W * 8, F)
     inp = t.get("inpaint_latents")
     with torch.no_grad():

@@ -108,9 +108,12 @@ def _load_case(name):
     return load_file(path), meta
 
 
-@pytest.mark.parametrize("name", ["vae_small_attn", "vae_small_noattn_ragged", "vae_full_arch"])
-def test_vae_decode_matches_reference_golden(name):
-    """decode() vs the output of the reference's own chunked Decoder (fp32 golden) and vs the oracle run in bf16."""
+GOLDEN_DECODE_CASES = ["vae_small_attn", "vae_small_noattn_ragged", "vae_full_arch"]
+
+
+def prelude_decode_golden(name):
+    """Everything of test_vae_decode_matches_reference_golden that needs no GPU (fixture, oracle pair, product module,
+    state-dict load and its key assertions); tests/test_gpu_preludes_cpu.py runs it on the authoring box."""
     from oracle import vae
     from easyanimate_b200.autoencoder_magvit import AutoencoderKLMagvit
     t, meta = _load_case(name)
@@ -130,7 +133,15 @@ def test_vae_decode_matches_reference_golden(name):
                                mid_block_attention_type="spatial", mid_block_use_attention=attn, mini_batch_decoder=1,
                                block_out_channels=boc, scaling_factor=0.7125).to(bf16)
     missing, unexpected = ours.load_state_dict(ob.state_dict(), strict=False)
-    assert not unexpected and all(k.startswith("quant_conv") for k in missing), (missing, unexpected)
+    # the decode-only oracle has no encoder / quant_conv: those (and only those) keys stay at their init values
+    assert not unexpected and all(k.startswith(("quant_conv", "encoder.")) for k in missing), (missing, unexpected)
+    return t, o32, ob, ours
+
+
+@pytest.mark.parametrize("name", GOLDEN_DECODE_CASES)
+def test_vae_decode_matches_reference_golden(name):
+    """decode() vs the output of the reference's own chunked Decoder (fp32 golden) and vs the oracle run in bf16."""
+    t, o32, ob, ours = prelude_decode_golden(name)
     ours = ours.cuda()
     z = t["z"].to(bf16)
     with torch.no_grad():
@@ -144,7 +155,7 @@ def test_vae_decode_matches_reference_golden(name):
     three_way(got, ref, truth, name=name)
 
 
-def test_vae_tiled_decode_matches_oracle():
+def prelude_tiled_oracle():
     from oracle import vae
     from easyanimate_b200.autoencoder_magvit import AutoencoderKLMagvit
     boc = [64, 64, 128, 128]
@@ -156,7 +167,13 @@ def test_vae_tiled_decode_matches_oracle():
     ours = AutoencoderKLMagvit(latent_channels=16, cache_mag_vae=True, spatial_group_norm=True,
                                mid_block_attention_type="spatial", block_out_channels=boc, use_tiling=True,
                                tile_sample_min_size=64).to(bf16)
-    ours.load_state_dict(ob.state_dict(), strict=False)
+    missing, unexpected = ours.load_state_dict(ob.state_dict(), strict=False)
+    assert not unexpected and all(k.startswith(("quant_conv", "encoder.")) for k in missing), (missing, unexpected)
+    return o32, ob, ours
+
+
+def test_vae_tiled_decode_matches_oracle():
+    o32, ob, ours = prelude_tiled_oracle()
     ours = ours.cuda()
     z = torch.randn(1, 16, 2, 12, 20, generator=torch.Generator().manual_seed(3)).to(bf16)
     with torch.no_grad():
@@ -171,16 +188,10 @@ def test_vae_tiled_decode_matches_oracle():
     assert torch.equal(got, again)
 
 
-def test_vae_tiled_decode_matches_reference_golden():
-    """Against the output of the REFERENCE's own AutoencoderKLMagvit.tiled_decode (fp32; tests/golden/make_golden.py::
-    make_vae_tiled): 3 x 3 ragged tiles + the lower-right corner pass."""
-    import ast
-    import os
-    from safetensors import safe_open
-    from safetensors.torch import load_file
+def prelude_tiled_reference_golden():
     from oracle import vae
     from easyanimate_b200.autoencoder_magvit import AutoencoderKLMagvit
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vae_ref_tiled.safetensors")
+    path = os.path.join(GOLD, "vae_ref_tiled.safetensors")
     t = load_file(path)
     with safe_open(path, framework="pt") as f:
         meta = f.metadata()
@@ -191,7 +202,15 @@ def test_vae_tiled_decode_matches_reference_golden():
     ob.load_state_dict({k: v.to(bf16) for k, v in o32.state_dict().items()})
     ours = AutoencoderKLMagvit(latent_channels=16, cache_mag_vae=True, spatial_group_norm=True, mid_block_attention_type="spatial",
                                **kw).to(bf16)
-    ours.load_state_dict(ob.state_dict(), strict=False)
+    missing, unexpected = ours.load_state_dict(ob.state_dict(), strict=False)
+    assert not unexpected and all(k.startswith(("quant_conv", "encoder.")) for k in missing), (missing, unexpected)
+    return t, ob, ours
+
+
+def test_vae_tiled_decode_matches_reference_golden():
+    """Against the output of the REFERENCE's own AutoencoderKLMagvit.tiled_decode (fp32; tests/golden/make_golden.py::
+    make_vae_tiled): 3 x 3 ragged tiles + the lower-right corner pass."""
+    t, ob, ours = prelude_tiled_reference_golden()
     ours = ours.cuda()
     with torch.no_grad():
         ref = ob.decode(t["z"].to(bf16))[0]

@@ -1,10 +1,8 @@
 """AutoencoderKLMagvit.encode on the GPU (I2V / inpaint conditioning prep).
 
-STATUS: written at the end of round 1, after the GPU budget of the round was spent - encode() composes kernels that are all
-validated elsewhere (tests/test_vae_gpu.py) and its host logic is checked on CPU against the oracle, which is pinned to the
-reference's Encoder (tests/test_host_logic_cpu.py, tests/test_oracle_cpu.py), but THESE tests have not run on a GPU yet.
-They are therefore non-strict xfail: a pass shows up as XPASS, a failure does not turn the suite red; the marker goes away
-with the first green GPU run."""
+encode() runs the encoder's stride-2 convolutions as the strided implicit-GEMM kernel (ea_conv3d_causal with stride fields)
+or, for A/B, as the stride-1 kernel plus a strided pick; both are compared here with fp32 PyTorch references and with the
+moments the REFERENCE's own AutoencoderKLMagvit.encode / tiled_encode produced (tests/golden/vae_ref_encode.safetensors)."""
 import ast
 import os
 
@@ -13,7 +11,7 @@ import torch
 
 from tests.parity import three_way
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first GPU run pending (written after the round's GPU budget was spent)")]
+pytestmark = pytest.mark.gpu
 bf16 = torch.bfloat16
 
 
@@ -36,8 +34,8 @@ def test_strided_convolution_as_stride1_plus_pick():
         torch.testing.assert_close(got.float(), ref, rtol=2 ** -7, atol=2e-2)
 
 
-def test_vae_encode_matches_reference_golden():
-    """Against the moments produced by the REFERENCE's AutoencoderKLMagvit.encode / tiled_encode (fp32, CPU)."""
+def prelude_encode_golden():
+    """The part of test_vae_encode_matches_reference_golden that needs no GPU (run on CPU by tests/test_gpu_preludes_cpu.py)."""
     from safetensors import safe_open
     from safetensors.torch import load_file
     from oracle import vae
@@ -53,6 +51,12 @@ def test_vae_encode_matches_reference_golden():
     ours = AutoencoderKLMagvit(latent_channels=16, cache_mag_vae=True, spatial_group_norm=True, mid_block_attention_type="spatial",
                                block_out_channels=boc).to(bf16)
     ours.load_state_dict(ob.state_dict(), strict=True)
+    return t, ob, ours
+
+
+def test_vae_encode_matches_reference_golden():
+    """Against the moments produced by the REFERENCE's AutoencoderKLMagvit.encode / tiled_encode (fp32, CPU)."""
+    t, ob, ours = prelude_encode_golden()
     ours = ours.cuda()
     x = t["x"].to(bf16)
     with torch.no_grad():
