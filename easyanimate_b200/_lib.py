@@ -116,7 +116,7 @@ ea_timestep_embedding = _sig("ea_timestep_embedding", [vp, vp, i64, i64, f32, i3
 ea_patchify = _sig("ea_patchify", [vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, vp])
 ea_unpatchify = _sig("ea_unpatchify", [vp, vp, i64, i64, i64, i64, i64, i64, vp])
 ea_attn_fwd = _sig("ea_attn_fwd", [C.POINTER(AttnArgs), vp])
-ea_transpose_v = _sig("ea_transpose_v", [vp, vp, i64, i64, i64, vp])
+ea_attn_generations = _sig("ea_attn_generations", [])
 ea_cfg_euler_step = _sig("ea_cfg_euler_step", [vp, vp, vp, vp, i64, f32, i32, f32, f32, vp])
 ea_l1_sums = _sig("ea_l1_sums", [vp, vp, vp, i64, vp])
 ea_ew_addsub = _sig("ea_ew_addsub", [vp, vp, vp, i64, i32, vp])

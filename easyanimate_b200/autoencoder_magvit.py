@@ -49,7 +49,7 @@ class _PackedConv(nn.Conv3d):
 
     def packed(self):
         w = self.weight
-        key = (w.data_ptr(), w._version, w.dtype, w.device)
+        key = ops.param_key(w)
         if self._packed is None or self._packed[0] != key:
             self._packed = (key, vae_ops.pack_conv_weight(w, self._cin_pad, self._cout_pad))
         return self._packed[1]
@@ -93,7 +93,7 @@ class _SpatialAttention(nn.Module):  # vaemodules/attention.py:63-160,391-423
 
     def _qkv(self):
         ps = (self.to_q.weight, self.to_k.weight, self.to_v.weight, self.to_q.bias, self.to_k.bias, self.to_v.bias)
-        key = tuple((p.data_ptr(), p._version) for p in ps)
+        key = ops.param_key(*ps)
         if self._fused is None or self._fused[0] != key:
             self._fused = (key, torch.cat([p.detach() for p in ps[:3]], 0).contiguous(),
                            torch.cat([p.detach() for p in ps[3:]], 0).contiguous())

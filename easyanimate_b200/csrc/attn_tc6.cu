@@ -518,11 +518,12 @@ static int launch(const ea_attn_args* g, cudaStream_t stream) {
   p.scale_log2 = g->scale * 1.4426950408889634f;
   p.dep_zero = 0;
   auto kern = attn6_kernel<POLY, PHASED, TRUNC>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static ::ea::PerDeviceFlag attr_flag;
+  const int attr_dev = ::ea::current_device();
+  if (!attr_flag.get(attr_dev)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kTotal);
     if (e != cudaSuccess) return fail(EA_ERR_CUDA, std::string("cudaFuncSetAttribute(attn6): ") + cudaGetErrorString(e));
-    attr_set = true;
+    attr_flag.set(attr_dev);
   }
   dim3 grid((unsigned)((g->S + 2 * kQT - 1) / (2 * kQT)), (unsigned)BH);
   kern<<<grid, kThreads, Smem::kTotal, stream>>>(tq, tk, tv, p);

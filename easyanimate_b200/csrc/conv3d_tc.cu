@@ -317,11 +317,12 @@ static int launch_conv(const ea_conv3d_args* g, cudaStream_t stream) {
     if (rc) return rc;
   }
   auto kern = conv3d_tc_kernel<BN, MT, PAIR>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static ::ea::PerDeviceFlag attr_flag;
+  const int attr_dev = ::ea::current_device();
+  if (!attr_flag.get(attr_dev)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return fail(EA_ERR_CUDA, std::string("cudaFuncSetAttribute(conv): ") + cudaGetErrorString(e));
-    attr_set = true;
+    attr_flag.set(attr_dev);
   }
   const int64_t num_tiles = (int64_t)p.T * p.tiles_h * p.tiles_w * p.tiles_n;
   if (num_tiles >= (1ll << 31)) return fail(EA_ERR_INVALID, "ea_conv3d: too many tiles");

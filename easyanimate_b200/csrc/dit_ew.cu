@@ -416,10 +416,11 @@ extern "C" int ea_skinny_linear(const ea_skinny_linear_args* g, void* stream_) {
   const size_t smem = (size_t)g->M * g->K * sizeof(float);
   EA_REQUIRE(smem <= 96 * 1024, "ea_skinny_linear: M*K too large for the shared-memory input stage");
   auto kern = skinny_linear_kernel<8>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static ::ea::PerDeviceFlag attr_flag;
+  const int attr_dev = ::ea::current_device();
+  if (!attr_flag.get(attr_dev)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_set = true;
+    attr_flag.set(attr_dev);
   }
   const int warps = 8;
   kern<<<(unsigned)((g->N + warps - 1) / warps), warps * 32, smem, stream>>>(

@@ -582,11 +582,12 @@ static int launch_gemm2(const void* a, int64_t lda, const void* w, int64_t ldw, 
     if (rc) return rc;
   }
   auto kern = gemm2_tc_kernel<EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static ::ea::PerDeviceFlag attr_flag;
+  const int attr_dev = ::ea::current_device();
+  if (!attr_flag.get(attr_dev)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return fail(EA_ERR_CUDA, std::string("cudaFuncSetAttribute(gemm2): ") + cudaGetErrorString(e));
-    attr_set = true;
+    attr_flag.set(attr_dev);
   }
   const int num_tiles = ((p.M + 2 * kBM - 1) / (2 * kBM)) * ((p.N + 255) / 256);
   const int clusters = num_tiles < sm_count() / 2 ? num_tiles : sm_count() / 2;
@@ -625,11 +626,12 @@ static int launch_gemm(const void* a, int64_t lda, const void* w, int64_t ldw, c
     if (rc) return rc;
   }
   auto kern = gemm_tc_kernel<BN, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static ::ea::PerDeviceFlag attr_flag;
+  const int attr_dev = ::ea::current_device();
+  if (!attr_flag.get(attr_dev)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return fail(EA_ERR_CUDA, std::string("cudaFuncSetAttribute(gemm): ") + cudaGetErrorString(e));
-    attr_set = true;
+    attr_flag.set(attr_dev);
   }
   const int num_tiles = ((p.M + kBM - 1) / kBM) * ((p.N + BN - 1) / BN);
   int grid = num_tiles < sm_count() ? num_tiles : sm_count();

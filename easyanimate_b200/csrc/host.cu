@@ -61,15 +61,25 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   return EA_OK;
 }
 
-int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
   }
-  return n;
+  return dev;
+}
+
+int sm_count() {
+  static int n[64] = {};
+  const int dev = current_device();
+  if (dev < 0 || dev >= 64) return 148;
+  if (n[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
+  }
+  return n[dev];
 }
 
 }  // namespace ea

@@ -21,7 +21,18 @@ int check_launch(const char* what);
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, bool swizzle128);
 
-int sm_count();
+int sm_count();  // of the CURRENT device (cached per device)
+int current_device();
+
+// "done once" state that is per DEVICE: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the current device
+// only, so a process that drives a second GPU (module.to("cuda:1") after work on cuda:0) must set it there too.
+struct PerDeviceFlag {
+  bool done[64] = {};
+  bool get(int dev) const { return dev >= 0 && dev < 64 && done[dev]; }
+  void set(int dev) {
+    if (dev >= 0 && dev < 64) done[dev] = true;
+  }
+};
 
 }  // namespace ea
 

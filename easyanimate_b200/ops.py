@@ -16,8 +16,9 @@ bf16 = torch.bfloat16
 ATTN_TIMING = None  # set to a list by bench.py to collect (start, end) CUDA events around every attention launch
 # attention kernel selector (include/ea_b200.h `ea_attn_args.variant`): 0x10c = sixth-generation kernel (one TMEM pass,
 # no per-block row maximum on the hot path, all exponentials on MUFU) — the fastest measured on B200
-# (profiles/r01_attn_microbench_*.log); 0x1c = fourth generation with 1 of 4 column pairs on the FMA pipe
+# (profiles/r01_attn_microbench_*.log).  The retired generations exist only in A/B builds (EA_ATTN_AB=1 build.sh).
 ATTN_VARIANT = int(os.environ.get("EA_ATTN_VARIANT", "0x10c"), 0)
+ATTN_GENERATIONS = L.ea_attn_generations()  # bit 6 always; bits 1, 4, 9 in A/B builds
 
 
 def _stream() -> int:
@@ -26,6 +27,19 @@ def _stream() -> int:
 
 def _p(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
+
+
+def param_key(*params) -> tuple:
+    """Cache key for derived copies of parameters (fused / packed weights): storage address, dtype, device and the in-place
+    version counter - which inference-mode tensors do not have (reading it raises), so it is optional."""
+    key = []
+    for p in params:
+        try:
+            ver = p._version
+        except Exception:
+            ver = -1
+        key.append((p.data_ptr(), ver, p.dtype, p.device))
+    return tuple(key)
 
 
 def _req(t: torch.Tensor, dtype=bf16, name="tensor"):
@@ -86,8 +100,11 @@ def skinny_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]
     N = w.shape[0]
     assert w.shape[1] == K and x.is_contiguous() and w.is_contiguous()
     out = torch.empty((M, N), device=x.device, dtype=bf16)
-    args = L.SkinnyArgs(x=_p(x), w=_p(w), bias=_p(bias), out=_p(out), M=M, N=N, K=K, act_in=act_in, act_out=act_out)
-    L.check(L.ea_skinny_linear(C.byref(args), _stream()), "ea_skinny_linear")
+    for m0 in range(0, M, 8):  # the kernel keeps up to 8 input rows in shared memory; larger batches go in row chunks
+        m = min(8, M - m0)
+        args = L.SkinnyArgs(x=x.data_ptr() + m0 * K * 2, w=_p(w), bias=_p(bias), out=out.data_ptr() + m0 * N * 2, M=m, N=N,
+                            K=K, act_in=act_in, act_out=act_out)
+        L.check(L.ea_skinny_linear(C.byref(args), _stream()), "ea_skinny_linear")
     return out
 
 
@@ -224,10 +241,12 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, S_text: int, *,
     if scale is None:
         scale = hd ** -0.5
     S_pad = 0
-    if variant & 2:
+    if (variant & 0x1102) == 2:  # A/B build only: first-generation kernel with a pre-transposed V
         S_pad = (S + 7) // 8 * 8
         vt = torch.empty((B, H, 64, S_pad), device=q.device, dtype=bf16)
-        L.check(L.ea_transpose_v(_p(v.contiguous()), _p(vt), B * H, S, S_pad, _stream()), "ea_transpose_v")
+        fn = L.lib.ea_transpose_v
+        fn.argtypes, fn.restype = [L.vp, L.vp, L.i64, L.i64, L.i64, L.vp], C.c_int
+        L.check(fn(_p(v.contiguous()), _p(vt), B * H, S, S_pad, _stream()), "ea_transpose_v")
         v = vt
     else:
         assert v.shape == q.shape and v.is_contiguous()

@@ -55,7 +55,7 @@ class _Attention(nn.Module):  # diffusers Attention(qk_norm="layer_norm", bias=T
     def fused_qkv(self):
         """[3d,d] weight / [3d] bias for the fused projection kernel; rebuilt when the parameters change."""
         ps = (self.to_q.weight, self.to_k.weight, self.to_v.weight, self.to_q.bias, self.to_k.bias, self.to_v.bias)
-        key = tuple((p.data_ptr(), p._version, p.dtype, p.device) for p in ps)
+        key = ops.param_key(*ps)
         if self._fused is None or self._fused[0] != key:
             w = torch.cat([p.detach() for p in ps[:3]], dim=0).contiguous()
             b = torch.cat([p.detach() for p in ps[3:]], dim=0).contiguous()
@@ -309,7 +309,7 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
 
     def _patch_weight(self, ldk: int) -> torch.Tensor:
         w = self.proj.weight
-        key = (w.data_ptr(), w._version, ldk)
+        key = ops.param_key(w) + (ldk,)
         if self._proj_w_cache is None or self._proj_w_cache[0] != key:
             w2 = w.detach().reshape(w.shape[0], -1)  # [d, C*4], K index = c*4 + ph*2 + pw
             if w2.shape[1] != ldk:

@@ -176,16 +176,14 @@ int ea_ew_addsub(const void* a, const void* b, void* out, int64_t n, int32_t sub
  * Replaces F.scaled_dot_product_attention + transpose/reshape/split at processor.py:287-303.
  * q,k,v: [B,H,S,64] bf16 contiguous.  Output is token-major and split at S_text:
  * out_text[B,S_text,H*64], out_video[B,S-S_text,H*64].
- * variant selects the kernel generation (all produce the same softmax; kept for A/B measurements, profiles/):
- *   bit8 (0x100; the Python layer's default is 0x10c): sixth generation - two query tiles per CTA, one TMEM pass,
- *     exponentials against the reference kept from earlier key blocks with an end-of-block overflow verdict instead of
- *     a per-block row maximum; bits 4-6: 0-3 = that many of every 4 column pairs by a polynomial on the FMA pipe instead
- *     of MUFU, 5/6 = 1/2 of 4 in two phases; bit11 (0x800): P packed by truncation instead of round-to-nearest;
- *   bit12 (0x1000): ninth generation - row sums from the tensor core, truncated P, 112-key blocks, bits 4-6 = 0-4 of
- *     every 8 pairs by polynomial;
- *   bits 2+3 (0x0c): fourth generation (per-block row maximum, lazy rescale), bits 4-6 = 0-4 polynomial pairs of 4;
- *   none of those: first-generation one-tile kernel - bit0: P operand through TMEM instead of shared memory,
- *   bit1: v is pre-transposed [B,H,64,S_pad] (see ea_transpose_v).  Anything else is EA_ERR_INVALID. */
+ * variant selects the kernel (all produce the same softmax):
+ *   0x10c (the Python layer's default): sixth generation - two query tiles per CTA, one TMEM pass, exponentials against
+ *     the reference kept from earlier key blocks with an end-of-block overflow verdict instead of a per-block row
+ *     maximum; bits 4-6: 0-3 = that many of every 4 column pairs by a polynomial on the FMA pipe instead of MUFU,
+ *     5/6 = 1/2 of 4 in two phases; bit11 (0x800): P packed by truncation instead of round-to-nearest.
+ *   Other values select retired generations (first: bits 0-1, fourth: 0x0c|poly<<4, ninth: 0x1000|...), present only in an
+ *   A/B build (EA_ATTN_AB=1 build.sh; tools/attn_ab/); ea_attn_generations() returns the bitmask of generations built
+ *   in (bit 6 always).  Anything else is EA_ERR_INVALID. */
 typedef struct {
   const void* q;
   const void* k;
@@ -198,9 +196,7 @@ typedef struct {
 } ea_attn_args;
 
 int ea_attn_fwd(const ea_attn_args* args, void* stream);
-
-/* v[BH,S,64] -> vt[BH,64,S_pad] (columns >= S zero-filled); S_pad % 8 == 0. */
-int ea_transpose_v(const void* v, void* vt, int64_t BH, int64_t S, int64_t S_pad, void* stream);
+int ea_attn_generations(void);
 
 /* ------------------------------------------------------------------------------------------------------------
  * MagViT VAE decode (AutoencoderKLMagvit.decode, autoencoder_magvit.py:271-317,381-448; Decoder,

@@ -9,7 +9,19 @@ bf16 = torch.bfloat16
 # all exponentials on MUFU); 0x11c / 0x12c: 1 / 2 of every 4 column pairs by the FMA-pipe polynomial; 0x15c / 0x16c: the
 # same in two phases; 0x90c: P by truncation; 0x100c-0x104c: ninth generation (tensor-core row sums, 112-key blocks,
 # 0..4 of 8 pairs by polynomial); 0x1c / 0x0c / 0x3c: fourth generation (per-block row maximum); 0-3: first generation
-VARIANTS = [0x10C, 0x11C, 0x12C, 0x15C, 0x16C, 0x90C, 0x100C, 0x101C, 0x102C, 0x104C, 0x1C, 0x0C, 0x3C, 0x1, 0x0, 0x3]
+# (the retired generations are tested only when the library was built with EA_ATTN_AB=1)
+def _variants(all_of):
+    from easyanimate_b200 import _lib
+    gens = _lib.ea_attn_generations()
+
+    def built(v):
+        if (v & 0x1100) == 0x100:
+            return True
+        return bool(gens & ((1 << 9) if v & 0x1000 else (1 << 4) if (v & 12) == 12 else (1 << 1)))
+    return [v for v in all_of if built(v)]
+
+
+VARIANTS = _variants([0x10C, 0x11C, 0x12C, 0x15C, 0x16C, 0x90C, 0x100C, 0x101C, 0x102C, 0x104C, 0x1C, 0x0C, 0x3C, 0x1, 0x0, 0x3])
 SHAPES = [(1, 2, 128, 0), (1, 2, 256, 64), (2, 3, 1000, 77), (1, 4, 4176, 256), (1, 1, 8, 3), (2, 2, 300, 300)]
 
 
@@ -50,7 +62,7 @@ def test_attention_large_logits_and_running_max_rescale():
         torch.testing.assert_close(ov.float(), ref, rtol=3e-2, atol=2e-2)
 
 
-@pytest.mark.parametrize("variant", [0x10C, 0x11C, 0x13C, 0x15C, 0x90C, 0x100C, 0x101C, 0x102C, 0x1C])
+@pytest.mark.parametrize("variant", _variants([0x10C, 0x11C, 0x13C, 0x15C, 0x90C, 0x100C, 0x101C, 0x102C, 0x1C]))
 @pytest.mark.parametrize("col,mag", [(640, 150.0), (643, 150.0), (640, 1500.0), (643, 1500.0), (130, 40.0), (1023, 800.0), (740, 1500.0), (700, 150.0)])
 def test_attention_outlier_key_beyond_the_kept_reference(variant, col, mag):
     """One key whose score exceeds everything before it by far more than 2^30 (in a polynomial-exp column, col % 8 < 2,

@@ -16,8 +16,8 @@
 // Template switches exist because two operand paths were brought up side by side on hardware:
 //   P_TMEM : P_j is the A operand from TMEM (tcgen05.mma [d],[a],b) instead of from shared memory
 //   V_TRANS: V is supplied pre-transposed ([B,H,64,S_pad], K-major B operand) instead of as an MN-major operand
-#include "common.cuh"
-#include "host.h"
+#include "../../easyanimate_b200/csrc/common.cuh"
+#include "../../easyanimate_b200/csrc/host.h"
 #include "../../include/ea_b200.h"
 
 namespace ea {
@@ -344,11 +344,12 @@ static int launch_attn(const ea_attn_args* g, cudaStream_t stream) {
   p.B = (int)g->B; p.H = (int)g->H; p.S = (int)g->S; p.S_text = (int)g->S_text;
   p.scale_log2 = g->scale * 1.4426950408889634f;
   auto kern = attn_fwd_kernel<P_TMEM, V_TRANS>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static ::ea::PerDeviceFlag attr_flag;
+  const int attr_dev = ::ea::current_device();
+  if (!attr_flag.get(attr_dev)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kTotal);
     if (e != cudaSuccess) return fail(EA_ERR_CUDA, std::string("cudaFuncSetAttribute(attn): ") + cudaGetErrorString(e));
-    attr_set = true;
+    attr_flag.set(attr_dev);
   }
   dim3 grid((unsigned)((g->S + kQT - 1) / kQT), (unsigned)BH);
   kern<<<grid, kAttnThreads, AttnSmem::kTotal, stream>>>(tq, tk, tv, p);
@@ -359,24 +360,8 @@ static int launch_attn(const ea_attn_args* g, cudaStream_t stream) {
 }  // namespace ea
 
 namespace ea {
-int launch_attn4(const ea_attn_args* g, int poly, cudaStream_t stream);
-int launch_attn6(const ea_attn_args* g, int poly, cudaStream_t stream);
-int launch_attn9(const ea_attn_args* g, int poly, cudaStream_t stream);
-}
-using namespace ea;
-
-extern "C" int ea_attn_fwd(const ea_attn_args* g, void* stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  EA_REQUIRE(g && g->q && g->k && g->v, "ea_attn_fwd: null pointer");
-  EA_REQUIRE(g->B > 0 && g->H > 0 && g->S > 0, "ea_attn_fwd: empty problem");
-  EA_REQUIRE(g->head_dim == 64, "ea_attn_fwd: head_dim must be 64");
-  EA_REQUIRE(g->S_text >= 0 && g->S_text <= g->S, "ea_attn_fwd: bad S_text");
-  EA_REQUIRE(g->S_text == 0 || g->out_text, "ea_attn_fwd: out_text missing");
-  EA_REQUIRE(g->S_text == g->S || g->out_video, "ea_attn_fwd: out_video missing");
-  EA_REQUIRE(g->B * g->H <= 65535, "ea_attn_fwd: B*H exceeds grid.y");
-  if (g->variant & 0x1000) return ea::launch_attn9(g, (g->variant >> 4) & 7, stream);  // tensor-core row sums, truncated P
-  if (g->variant & 0x100) return ea::launch_attn6(g, (g->variant >> 4) & 7, stream);   // optimistic reference (default)
-  if ((g->variant & 12) == 12) return ea::launch_attn4(g, (g->variant >> 4) & 7, stream);  // per-block row maximum
+// first-generation kernel behind ea_attn_fwd's variants 0-3 (A/B builds only, see easyanimate_b200/csrc/attn_api.cu)
+int launch_attn1(const ea_attn_args* g, cudaStream_t stream) {
   EA_REQUIRE((g->variant & ~3) == 0, "ea_attn_fwd: unknown kernel variant");
   const bool vt = (g->variant & 2) != 0, pt = (g->variant & 1) != 0;
   if (vt) EA_REQUIRE(g->S_pad >= g->S && g->S_pad % 8 == 0, "ea_attn_fwd: S_pad must be >= S and a multiple of 8");
@@ -385,6 +370,7 @@ extern "C" int ea_attn_fwd(const ea_attn_args* g, void* stream_) {
   if (!pt && vt) return launch_attn<false, true>(g, stream);
   return launch_attn<true, true>(g, stream);
 }
+}  // namespace ea
 
 namespace ea {
 __global__ void transpose_v_kernel(const bf16* __restrict__ v, bf16* __restrict__ vt, int S, int S_pad) {

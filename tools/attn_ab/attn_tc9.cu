@@ -27,8 +27,8 @@
 //   warps 0-3 / 4-7 : softmax of tile A / B, one query row per thread (setmaxnreg 232)
 //   warp 8          : TMA producer (Q once, K_j / V_j 112-key tiles through 4-stage rings)
 //   warps 9 / 10    : MMA issuer of tile A / B (9 also owns the TMEM allocation);  warp 11: fills the all-ones tile
-#include "common.cuh"
-#include "host.h"
+#include "../../easyanimate_b200/csrc/common.cuh"
+#include "../../easyanimate_b200/csrc/host.h"
 #include "../../include/ea_b200.h"
 
 namespace ea {
@@ -477,11 +477,12 @@ static int launch(const ea_attn_args* g, cudaStream_t stream) {
   p.B = (int)g->B; p.H = (int)g->H; p.S = (int)g->S; p.S_text = (int)g->S_text;
   p.scale_log2 = g->scale * 1.4426950408889634f;
   auto kern = attn9_kernel<POLY8>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static ::ea::PerDeviceFlag attr_flag;
+  const int attr_dev = ::ea::current_device();
+  if (!attr_flag.get(attr_dev)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kTotal);
     if (e != cudaSuccess) return fail(EA_ERR_CUDA, std::string("cudaFuncSetAttribute(attn9): ") + cudaGetErrorString(e));
-    attr_set = true;
+    attr_flag.set(attr_dev);
   }
   dim3 grid((unsigned)((g->S + 2 * kQT - 1) / (2 * kQT)), (unsigned)BH);
   kern<<<grid, kThreads, Smem::kTotal, stream>>>(tq, tk, tv, p);
