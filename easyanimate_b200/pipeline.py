@@ -129,11 +129,11 @@ class EasyAnimateSampler:
         return self._euler(pred, latents, self.guidance_scale, sigma, sigma_next, use_cfg=True)
 
     def step_from_host(self, latents_host: torch.Tensor, i: int, embeds_host: torch.Tensor, rope,
-                       out_host: Optional[torch.Tensor] = None, device="cuda") -> torch.Tensor:
+                       out_host: Optional[torch.Tensor] = None, device="cuda", inpaint_latents=None) -> torch.Tensor:
         """Same step with HOST (pinned) inputs and output: H2D of the step's inputs and D2H of its result included."""
         lat = latents_host.to(device, non_blocking=True)
         emb = embeds_host.to(device, non_blocking=True)
-        new = self.step(lat, i, emb, rope)
+        new = self.step(lat, i, emb, rope, inpaint_latents)
         if out_host is None:
             out_host = torch.empty(new.shape, dtype=new.dtype, pin_memory=True)
         out_host.copy_(new, non_blocking=True)
