@@ -93,7 +93,7 @@ class ConvArgs(C.Structure):
     _fields_ = [
         ("x", vp), ("w", vp), ("bias", vp), ("residual", vp), ("out", vp),
         ("T", i64), ("H", i64), ("W", i64), ("Cin", i64), ("Cout", i64), ("Cout_pad", i64),
-        ("dup_frames", i32), ("out_planar", i32), ("variant", i32),
+        ("dup_frames", i32), ("out_planar", i32), ("variant", i32), ("stride_t", i32), ("stride_hw", i32),
     ]
 
 

@@ -9,11 +9,11 @@ layer (the reference's per-latent-frame loop with conv caches, omnigen_enc_dec.p
 arithmetically the same convolution), per-frame GroupNorm+SiLU kernels, tcgen05 GEMMs for the 1x1x1 shortcuts and
 the mid-block spatial attention.
 
-``encode`` (I2V / inpaint conditioning prep) runs on the SAME validated kernels: the
-encoder's stride-2 convolutions (downsamplers.py:24-96) are executed as the stride-1 causal convolution followed by a
-strided pick (output (t, i, j) of the strided conv == output (2t, 2i+1, 2j+1) of the stride-1 one), which wastes 4-8x of
-the FLOPs of those three layers but needs no new kernel.  STATUS: host logic checked on CPU against the oracle, which is
-pinned to the reference's Encoder (tests/test_host_logic_cpu.py); first GPU run pending (tests/test_zz_vae_encode_gpu.py).
+``encode`` (I2V / inpaint conditioning prep) runs on the same kernels: the encoder's
+stride-2 convolutions (downsamplers.py:24-96) are the implicit-GEMM kernel with TMA element strides (no wasted FLOPs); the
+stride-1 kernel + strided pick (output (t, i, j) of the strided conv == output (2t, 2i+1, 2j+1) of the stride-1 one) stays
+as an A/B path (EA_ENC_STRIDED=0).  Host logic is checked on CPU against the oracle, which is pinned to the reference's
+Encoder (tests/test_host_logic_cpu.py); GPU parity against the reference-minted fixture in tests/test_zz_vae_encode_gpu.py.
 """
 from __future__ import annotations
 
@@ -192,10 +192,15 @@ class _Downsampler(nn.Module):  # downsamplers.py:24-46 (spatial), :74-96 (spati
         self.conv = _PackedConv(channels, channels)
         self.temporal = temporal
 
+    strided_kernel = os.environ.get("EA_ENC_STRIDED", "1") != "0"  # 0: stride-1 kernel + strided pick (A/B, 4-8x the FLOPs)
+
     def run(self, x):
         # CausalConv3d(kernel 3, stride (s_t, 2, 2), no spatial padding) after F.pad(x, (0,1,0,1)): output (t,i,j) reads
-        # frames 2t-2..2t (clamped at 0) and pixels 2i..2i+2 / 2j..2j+2 with zeros past the right/bottom edge - exactly
-        # output (s_t*t, 2i+1, 2j+1) of the stride-1 causal convolution with 1-pixel zero padding that the kernel computes.
+        # frames 2t-2..2t (clamped at 0) and pixels 2i..2i+2 / 2j..2j+2 with zeros past the right/bottom edge.  The
+        # implicit-GEMM kernel does that directly (TMA element strides, ea_conv3d_args.stride_*); it is also output
+        # (s_t*t, 2i+1, 2j+1) of the stride-1 causal convolution with 1-pixel zero padding, which the A/B path picks from.
+        if self.strided_kernel:
+            return self.conv.run(x, stride_t=2 if self.temporal else 1, stride_hw=2)
         y = self.conv.run(x)
         if self.temporal:
             y = y[::2]

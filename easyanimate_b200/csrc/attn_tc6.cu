@@ -30,9 +30,7 @@ extern void count_launch();
 
 namespace a6 {
 
-constexpr int kThreads = 384;
 constexpr int kQT = 128;
-constexpr int kKT = 128;
 constexpr int kHD = 64;
 constexpr int kStages = 4;
 
@@ -44,15 +42,26 @@ struct Args {
   uint32_t dep_zero;  // always 0; a value the compiler cannot see through (exp_row_phased)
 };
 
-struct Smem {
-  static constexpr int kQBytes = 2 * kQT * kHD * 2;
-  static constexpr int kKBytes = kKT * kHD * 2;
-  static constexpr int kVBytes = kKT * kHD * 2;
+// NT query tiles of 128 rows per CTA, key blocks of KT keys.  (2, 128): the layout described above.  (3, 64): three softmax
+// warps per SM sub-partition instead of two (more independent instruction streams to keep the MUFU queue fed across the
+// block-boundary latencies: barrier wait, first TMEM load, verdict, P-store completion), at half the work per block.
+template <int NT, int KT>
+struct Cfg {
+  static constexpr int kThreads = 128 * NT + 128;
+  static constexpr int kQBytes = NT * kQT * kHD * 2;
+  static constexpr int kKBytes = KT * kHD * 2;
+  static constexpr int kVBytes = KT * kHD * 2;
   static constexpr int kOffQ = 0;
   static constexpr int kOffK = kOffQ + kQBytes;
   static constexpr int kOffV = kOffK + kStages * kKBytes;
   static constexpr int kOffBar = kOffV + kStages * kVBytes;
   static constexpr int kTotal = kOffBar + 512 + 1024;
+  // TMEM columns: S_t (KT fp32 columns each) | P_t (KT/2 columns of packed bf16 pairs) | O_t (64)
+  static constexpr uint32_t kColP = NT * KT;
+  static constexpr uint32_t kColO = kColP + NT * (KT / 2);
+  static_assert(kColO + NT * kHD <= 512, "TMEM budget");
+  // registers: the producer/MMA warpgroup shrinks to 40, the softmax warpgroups grow to kSoftmaxRegs
+  static constexpr int kSoftmaxRegs = NT == 2 ? 232 : 152;
 };
 
 EA_DEVICE void tmem_st16(uint32_t taddr, const uint32_t* r) {
@@ -194,34 +203,38 @@ EA_DEVICE void exp_row_phased(const uint32_t* s, float2 c2, float2 nm2, float2* 
   }
 }
 
-template <int POLY, bool PHASED, bool TRUNC>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int POLY, bool PHASED, bool TRUNC, int NT, int KT>
+__global__ void __launch_bounds__(Cfg<NT, KT>::kThreads, 1)
 attn6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
              const __grid_constant__ CUtensorMap tmap_v, const Args p) {
+  using C = Cfg<NT, KT>;
+  static_assert(!PHASED || (NT == 2 && KT == 128), "the two-phase variant exists for the 2 x 128 layout only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem + Smem::kOffQ;
-  uint8_t* sK = smem + Smem::kOffK;
-  uint8_t* sV = smem + Smem::kOffV;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::kOffBar);
+  uint8_t* sQ = smem + C::kOffQ;
+  uint8_t* sK = smem + C::kOffK;
+  uint8_t* sV = smem + C::kOffV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;
   uint64_t* k_empty = k_full + kStages;
   uint64_t* v_full = k_empty + kStages;
   uint64_t* v_empty = v_full + kStages;
   uint64_t* s_full = v_empty + kStages;   // [tile]
-  uint64_t* s_free = s_full + 2;          // [tile]
-  uint64_t* p_ready = s_free + 2;         // [tile]
-  uint64_t* o_done = p_ready + 2;         // [tile]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* s_free = s_full + NT;         // [tile]
+  uint64_t* p_ready = s_free + NT;        // [tile]
+  uint64_t* o_done = p_ready + NT;        // [tile]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + NT);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * (2 * kQT);
+  const int q0 = blockIdx.x * (NT * kQT);
   const int bh = blockIdx.y;
-  const int nblk = (p.S + kKT - 1) / kKT;
+  const int nblk = (p.S + KT - 1) / KT;
+  constexpr int kProducerWarp = 4 * NT;      // then one MMA issuer warp per tile
+  constexpr int kFirstIssuer = 4 * NT + 1;
 
-  constexpr uint32_t kColP = 256, kColO = 384;
+  constexpr uint32_t kColP = C::kColP, kColO = C::kColO;
   constexpr uint32_t kTmemCols = 512;
 
   if (threadIdx.x == 0) {
@@ -231,11 +244,11 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     mbar_init(q_full, 1);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 2);  // one tcgen05.commit per tile issuer
+      mbar_init(&k_empty[i], NT);  // one tcgen05.commit per tile issuer
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 2);
+      mbar_init(&v_empty[i], NT);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NT; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_free[i], 128);
       mbar_init(&p_ready[i], 128);
@@ -243,65 +256,66 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     }
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == kFirstIssuer) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 8) {
+  if (warp >= kProducerWarp) {
   // ---- producer / MMA warpgroup: give registers back
   asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-  if (warp == 8) {
+  if (warp == kProducerWarp) {
     if (lane == 0) {
       // ===== TMA producer =====
-      mbar_arrive_expect_tx(q_full, Smem::kQBytes);
-      tma_load_3d(sQ, &tmap_q, q_full, 0, q0, bh);
+      mbar_arrive_expect_tx(q_full, C::kQBytes);
+#pragma unroll
+      for (int t = 0; t < NT; ++t) tma_load_3d(sQ + t * (kQT * kHD * 2), &tmap_q, q_full, 0, q0 + t * kQT, bh);
       int st = 0;
       uint32_t ph = 0;
       for (int j = 0; j < nblk; ++j) {
         mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], Smem::kKBytes);
-        tma_load_3d(sK + st * Smem::kKBytes, &tmap_k, &k_full[st], 0, j * kKT, bh);
+        mbar_arrive_expect_tx(&k_full[st], C::kKBytes);
+        tma_load_3d(sK + st * C::kKBytes, &tmap_k, &k_full[st], 0, j * KT, bh);
         mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], Smem::kVBytes);
-        tma_load_3d(sV + st * Smem::kVBytes, &tmap_v, &v_full[st], 0, j * kKT, bh);
+        mbar_arrive_expect_tx(&v_full[st], C::kVBytes);
+        tma_load_3d(sV + st * C::kVBytes, &tmap_v, &v_full[st], 0, j * KT, bh);
         if (++st == kStages) { st = 0; ph ^= 1; }
       }
     }
-  } else if (warp <= 10) {
+  } else if (warp < kFirstIssuer + NT) {
     if (lane == 0) {
-      // ===== MMA issuers: warp 9 drives tile A, warp 10 drives tile B, independently =====
-      // (one issuer walking both tiles in a fixed order head-of-line blocks: it sits in wait(p_ready[A]) while
+      // ===== MMA issuers: one warp per query tile, independently =====
+      // (one issuer walking the tiles in a fixed order head-of-line blocks: it sits in wait(p_ready[A]) while
       //  s_free[B] has long fired, the tiles lock IN phase and the TMEM-read and exp phases never overlap.)
-      const int t = warp - 9;
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(kQT, kKT, 0, 0);
+      const int t = warp - kFirstIssuer;
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(kQT, KT, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(kQT, kHD, 0, 1);  // V: MN-major B operand
       mbar_wait(q_full, 0);
       tc_fence_after();
       auto issue_qk = [&](int t, int j) {
         const int st = j % kStages;
         const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ + t * (kQT * kHD * 2)));
-        const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + st * Smem::kKBytes));
-        const uint32_t d = tmem_base + t * kKT;
+        const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + st * C::kKBytes));
+        const uint32_t d = tmem_base + t * KT;
 #pragma unroll
         for (int k = 0; k < kHD / 16; ++k) umma_ss(d, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
         umma_commit(&s_full[t]);
       };
       auto issue_pv = [&](int t, int j) {
         const int st = j % kStages;
-        const uint32_t vaddr = smem_u32(sV + st * Smem::kVBytes);
+        const uint32_t vaddr = smem_u32(sV + st * C::kVBytes);
         const uint32_t d = tmem_base + kColO + t * kHD;
-        const uint32_t pa = tmem_base + kColP + t * 64;
+        const uint32_t pa = tmem_base + kColP + t * (KT / 2);
 #pragma unroll
-        for (int k = 0; k < kKT / 16; ++k)
-          umma_ts(d, pa + k * 8, umma_desc_sw128_mn(vaddr + k * 2048, 16384, 1024), idesc_pv, (j | k) != 0);
+        for (int k = 0; k < KT / 16; ++k)
+          umma_ts(d, pa + k * 8, umma_desc_sw128_mn(vaddr + k * 2048, C::kVBytes, 1024), idesc_pv, (j | k) != 0);
         umma_commit(&o_done[t]);
       };
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
       issue_qk(t, 0);
-      umma_commit(&k_empty[0]);  // K/V stages are released when BOTH issuers have committed (barrier count 2)
+      umma_commit(&k_empty[0]);  // K/V stages are released when ALL issuers have committed (barrier count NT)
       for (int j = 0; j < nblk; ++j) {
         const int st = j % kStages;
         const uint32_t par = j & 1;
@@ -322,31 +336,32 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
   }
   } else {
     // ---- softmax warpgroups: take them
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    if constexpr (NT == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
     // ===== softmax / correction / epilogue: tile t, one query row per thread =====
     const int t = warp >> 2;
     const int ew = warp & 3;
     const int r = ew * 32 + lane;
     const uint32_t lane_off = uint32_t(ew * 32) << 16;
-    const uint32_t tS = tmem_base + lane_off + t * kKT;
-    const uint32_t tP = tmem_base + lane_off + kColP + t * 64;
+    const uint32_t tS = tmem_base + lane_off + t * KT;
+    const uint32_t tP = tmem_base + lane_off + kColP + t * (KT / 2);
     const uint32_t tO = tmem_base + lane_off + kColO + t * kHD;
-    const uint32_t bar_t = opaque(smem_u32(&s_full[t]));  // s_full[t]; s_free[t] +16, p_ready[t] +32, o_done[t] +48
-    constexpr uint32_t kSFree = 16, kPReady = 32, kODone = 48;
+    const uint32_t bar_t = opaque(smem_u32(&s_full[t]));  // s_full[t]; s_free[t], p_ready[t], o_done[t] follow at 8*NT strides
+    constexpr uint32_t kSFree = 8 * NT, kPReady = 16 * NT, kODone = 24 * NT;
     float m_ref = 0.f;
     float l = 0.f;
     const float2 c2 = make_float2(p.scale_log2, p.scale_log2);
     for (int j = 0; j < nblk; ++j) {
       bar_wait(bar_t, j & 1);
-      // start the two tiles half a period apart (see attn_tc4.cu)
-      if (t == 1 && j == 0) mbar_wait(&s_free[0], 0);
+      // start the tiles a fraction of a period apart: tile t's first block begins when tile t-1 has pulled its scores
+      if (t > 0 && j == 0) mbar_wait(&s_free[t - 1], 0);
       tc_fence_after();
-      uint32_t s[kKT];
+      uint32_t s[KT];
       uint32_t pk[16], pk2[16];
-      const int valid = p.S - j * kKT;  // < 128 only in the last block (TMA zero-filled the missing keys)
+      const int valid = p.S - j * KT;  // < KT only in the last block (TMA zero-filled the missing keys)
       float2 acc2[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
       float guard = -INFINITY;
-      bool redo = (j == 0) || (valid < kKT);
+      bool redo = (j == 0) || (valid < KT);
       if (!redo) {
         // ---- fast pass: exponentiate against the reference kept from earlier blocks.  The P stores trail the
         // exponentials by one chunk so that the wait for PV_{j-1} (which reads P_t) sits in the middle of the block.
@@ -370,7 +385,7 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
           tmem_st16(tP + 16, pkr + 16);
           tmem_st16(tP + 32, pkr + 32);
           tmem_st16(tP + 48, pkr + 48);
-        } else {
+        } else if constexpr (KT == 128) {
           tmem_ld32p(tS, s);
           tmem_ld_fence(s);
           tmem_ld32p(tS + 32, s + 32);
@@ -392,22 +407,35 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
           tmem_st16(tP + 32, pk);
           exp_pairs<POLY, 0, 16, TRUNC>(s + 96, c2, nm2, acc2, guard, pk2);
           tmem_st16(tP + 48, pk2);
+        } else {
+          static_assert(KT == 64 || KT == 128, "key block of 64 or 128");
+          tmem_ld32p(tS, s);
+          tmem_ld_fence(s);
+          tmem_ld32p(tS + 32, s + 32);
+          exp_pairs<POLY, 0, 16, TRUNC>(s, c2, nm2, acc2, guard, pk);
+          tmem_ld_fence(s + 32);
+          tc_fence_before();
+          bar_arrive(bar_t + kSFree);  // S_t may be overwritten by QK_{j+1}
+          exp_pairs<POLY, 0, 8, TRUNC>(s + 32, c2, nm2, acc2, guard, pk2);
+          bar_wait(bar_t + kODone, (j - 1) & 1);  // PV_{j-1} has read P_t
+          tc_fence_after();
+          tmem_st16(tP, pk);
+          exp_pairs<POLY, 8, 16, TRUNC>(s + 32, c2, nm2, acc2, guard, pk2);
+          tmem_st16(tP + 16, pk2);
         }
         const float l_blk = ((acc2[0].x + acc2[0].y) + (acc2[1].x + acc2[1].y)) + ((acc2[2].x + acc2[2].y) + (acc2[3].x + acc2[3].y));
         const bool ok = (l_blk <= 1073741824.0f) && (POLY == 0 || fmaf(guard, p.scale_log2, -m_ref) <= 64.0f);
         redo = __any_sync(0xffffffffu, !ok);
         if (!redo) l += l_blk;
       } else {
-        tmem_ld32p(tS, s);
-        tmem_ld32p(tS + 32, s + 32);
-        tmem_ld32p(tS + 64, s + 64);
-        tmem_ld32p(tS + 96, s + 96);
+#pragma unroll
+        for (int c = 0; c < KT / 32; ++c) tmem_ld32p(tS + c * 32, s + c * 32);
         tmem_ld_wait();
         tc_fence_before();
         bar_arrive(bar_t + kSFree);
-        if (valid < kKT) {
+        if (valid < KT) {
 #pragma unroll
-          for (int i = 0; i < kKT; ++i)
+          for (int i = 0; i < KT; ++i)
             if (i >= valid) s[i] = 0xff800000u;  // -inf
         }
       }
@@ -416,7 +444,7 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         // row whose scores outgrew the reference by more than 2^30)
         float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int i = 0; i < kKT; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(s[i]));
+        for (int i = 0; i < KT; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(s[i]));
         const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
         if (j == 0) {
           m_ref = mx;
@@ -442,12 +470,12 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc2[i] = make_float2(0.f, 0.f);
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          // (rare path: keep it small - rotate the score registers instead of unrolling four copies)
+        for (int c = 0; c < KT / 32; ++c) {
+          // (rare path: keep it small - rotate the score registers instead of unrolling the chunks)
           exp_pairs<POLY, 0, 16, TRUNC>(s, c2, nm2, acc2, guard, pk);
           tmem_st16(tP + c * 16, pk);
 #pragma unroll
-          for (int i = 0; i < 96; ++i) s[i] = s[i + 32];
+          for (int i = 0; i < KT - 32; ++i) s[i] = s[i + 32];
         }
         l += ((acc2[0].x + acc2[0].y) + (acc2[1].x + acc2[1].y)) + ((acc2[2].x + acc2[2].y) + (acc2[3].x + acc2[3].y));
       }
@@ -490,21 +518,22 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == kFirstIssuer) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
-template <int POLY, bool PHASED, bool TRUNC>
+template <int POLY, bool PHASED, bool TRUNC, int NT = 2, int KT = 128>
 static int launch(const ea_attn_args* g, cudaStream_t stream) {
+  using C = Cfg<NT, KT>;
   const int64_t BH = g->B * g->H;
   CUtensorMap tq, tk, tv;
   uint64_t dims[3] = {(uint64_t)kHD, (uint64_t)g->S, (uint64_t)BH};
   uint64_t strides[2] = {(uint64_t)kHD * 2, (uint64_t)g->S * kHD * 2};
-  uint32_t box_q[3] = {kHD, 2 * kQT, 1};
-  uint32_t box_kv[3] = {kHD, kKT, 1};
+  uint32_t box_q[3] = {kHD, kQT, 1};
+  uint32_t box_kv[3] = {kHD, KT, 1};
   int rc = make_tmap_bf16(&tq, g->q, 3, dims, strides, box_q, true);
   if (rc) return rc;
   rc = make_tmap_bf16(&tk, g->k, 3, dims, strides, box_kv, true);
@@ -517,16 +546,16 @@ static int launch(const ea_attn_args* g, cudaStream_t stream) {
   p.B = (int)g->B; p.H = (int)g->H; p.S = (int)g->S; p.S_text = (int)g->S_text;
   p.scale_log2 = g->scale * 1.4426950408889634f;
   p.dep_zero = 0;
-  auto kern = attn6_kernel<POLY, PHASED, TRUNC>;
+  auto kern = attn6_kernel<POLY, PHASED, TRUNC, NT, KT>;
   static ::ea::PerDeviceFlag attr_flag;
   const int attr_dev = ::ea::current_device();
   if (!attr_flag.get(attr_dev)) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal);
     if (e != cudaSuccess) return fail(EA_ERR_CUDA, std::string("cudaFuncSetAttribute(attn6): ") + cudaGetErrorString(e));
     attr_flag.set(attr_dev);
   }
-  dim3 grid((unsigned)((g->S + 2 * kQT - 1) / (2 * kQT)), (unsigned)BH);
-  kern<<<grid, kThreads, Smem::kTotal, stream>>>(tq, tk, tv, p);
+  dim3 grid((unsigned)((g->S + NT * kQT - 1) / (NT * kQT)), (unsigned)BH);
+  kern<<<grid, C::kThreads, C::kTotal, stream>>>(tq, tk, tv, p);
   count_launch();
   return check_launch("attn6_kernel");
 }
@@ -535,6 +564,13 @@ static int launch(const ea_attn_args* g, cudaStream_t stream) {
 
 int launch_attn6(const ea_attn_args* g, int poly, cudaStream_t stream) {
   const bool trunc = (g->variant & 0x800) != 0;  // experimental: P by truncation (PRMT) instead of F2FP round-to-nearest
+  if (g->variant & 0x2000) {  // three query tiles per CTA, 64-key blocks
+    switch (poly) {
+      case 0: return trunc ? a6::launch<0, false, true, 3, 64>(g, stream) : a6::launch<0, false, false, 3, 64>(g, stream);
+      case 1: return a6::launch<1, false, false, 3, 64>(g, stream);
+      default: return fail(EA_ERR_INVALID, "ea_attn_fwd: the 3 x 64 layout takes 0 or 1 polynomial pairs of 4");
+    }
+  }
   switch (poly) {
     case 0: return trunc ? a6::launch<0, false, true>(g, stream) : a6::launch<0, false, false>(g, stream);
     case 1: return trunc ? a6::launch<1, false, true>(g, stream) : a6::launch<1, false, false>(g, stream);

@@ -41,6 +41,7 @@ struct ConvDevArgs {
   int dup_frames;
   int out_planar;
   int T_out;
+  int st, shw;  // temporal / spatial stride (1 or 2): T, H, W above are the OUTPUT extents (see ea_conv3d_args.stride_*)
 };
 
 template <int BN, int MT, bool PAIR = false>
@@ -125,17 +126,22 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           const int tap = kb / cchunks;
           const int c0 = (kb - tap * cchunks) * kCK;
           const int kt = tap / 9, kh = (tap % 9) / 3, kw = tap % 3;
-          int tin = t + kt - (p.kt_taps - 1);  // causal: taps reach back in time; left edge replicates frame 0
+          int tin = t * p.st + kt - (p.kt_taps - 1);  // causal: taps reach back in time; left edge replicates frame 0
           tin = tin < 0 ? 0 : tin;
+          // stride 1: 1-pixel zero border on every side (x = w0 + kw - 1).  stride 2 (downsamplers.py:24-96: F.pad right /
+          // bottom by one, no padding in the convolution): output (i, j) reads input rows 2i..2i+2, columns 2j..2j+2, and the
+          // tensor map walks the box with element stride 2, so one box still lands as TH x TW consecutive GEMM rows.
+          const int xw = p.shw == 1 ? w0 + kw - 1 : 2 * w0 + kw;
+          const int xh = p.shw == 1 ? h0 + kh - 1 : 2 * h0 + kh;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (PAIR) {
             const uint32_t lfull = mapa_shared(smem_u32(&full_bar[stage]), 0);
             mbar_arrive_expect_tx_cluster(lfull, Cfg::kStageBytes);
-            tma_load_4d_2sm(smem_a + stage * Cfg::kABytes, &tmap_x, lfull, c0, w0 + kw - 1, h0 + kh - 1, tin);
+            tma_load_4d_2sm(smem_a + stage * Cfg::kABytes, &tmap_x, lfull, c0, xw, xh, tin);
             tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &tmap_w, lfull, tap * p.Cin + c0, n0 + crank * (BN / 2));
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_x, &full_bar[stage], c0, w0 + kw - 1, h0 + kh - 1, tin);
+            tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_x, &full_bar[stage], c0, xw, xh, tin);
             tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_w, &full_bar[stage], tap * p.Cin + c0, n0);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -282,7 +288,13 @@ template <int BN, int MT, bool PAIR = false>
 static int launch_conv(const ea_conv3d_args* g, cudaStream_t stream) {
   using Cfg = ConvCfg<BN, MT, PAIR>;
   ConvDevArgs p{};
-  p.T = (int)g->T; p.H = (int)g->H; p.W = (int)g->W; p.Cin = (int)g->Cin; p.Cout = (int)g->Cout;
+  p.st = g->stride_t == 2 ? 2 : 1;
+  p.shw = g->stride_hw == 2 ? 2 : 1;
+  // output extents: every second frame from frame 0 (T = 1 + 2m -> m + 1), floor(H / 2) x floor(W / 2) pixels
+  p.T = p.st == 2 ? (int)((g->T + 1) / 2) : (int)g->T;
+  p.H = p.shw == 2 ? (int)(g->H / 2) : (int)g->H;
+  p.W = p.shw == 2 ? (int)(g->W / 2) : (int)g->W;
+  p.Cin = (int)g->Cin; p.Cout = (int)g->Cout;
   // tile shape: 8x16 or 4x32 pixels, whichever wastes fewer out-of-range pixels
   auto waste = [&](int th, int tw) {
     th *= MT * (PAIR ? 2 : 1);
@@ -298,14 +310,17 @@ static int launch_conv(const ea_conv3d_args* g, cudaStream_t stream) {
   p.out = reinterpret_cast<bf16*>(g->out);
   p.dup_frames = g->dup_frames;
   p.out_planar = g->out_planar;
-  p.T_out = g->dup_frames ? (int)(2 * g->T - 1) : (int)g->T;
+  p.T_out = g->dup_frames ? (int)(2 * g->T - 1) : p.T;
 
   CUtensorMap tx, tw;
   {
     uint64_t dims[4] = {(uint64_t)g->Cin, (uint64_t)g->W, (uint64_t)g->H, (uint64_t)g->T};
     uint64_t strides[3] = {(uint64_t)g->Cin * 2, (uint64_t)g->W * g->Cin * 2, (uint64_t)g->H * g->W * g->Cin * 2};
-    uint32_t box[4] = {kCK, (uint32_t)p.TW, (uint32_t)(MT * p.TH), 1};  // MT sub-tiles stacked along H
-    int rc = make_tmap_bf16(&tx, g->x, 4, dims, strides, box, true);
+    // MT sub-tiles stacked along H; with a spatial stride the box spans shw x as many input elements, walked with element
+    // stride shw (cuTensorMapEncodeTiled elementStrides): the number of elements that land is still TW x MT*TH
+    uint32_t box[4] = {kCK, (uint32_t)(p.TW * p.shw), (uint32_t)(MT * p.TH * p.shw), 1};
+    uint32_t estr[4] = {1, (uint32_t)p.shw, (uint32_t)p.shw, 1};
+    int rc = make_tmap_bf16(&tx, g->x, 4, dims, strides, box, true, estr);
     if (rc) return rc;
   }
   {
@@ -365,9 +380,18 @@ extern "C" int ea_conv3d_causal(const ea_conv3d_args* g, void* stream_) {
   EA_REQUIRE(g->out_planar || g->Cout % 32 == 0, "ea_conv3d_causal: channels-last output needs Cout % 32 == 0");
   EA_REQUIRE(!(g->out_planar && g->residual), "ea_conv3d_causal: planar output cannot take a residual");
   EA_REQUIRE(g->W < 32768 && g->H < 32768, "ea_conv3d_causal: frame too large");
+  EA_REQUIRE((g->stride_t == 0 || g->stride_t == 1 || g->stride_t == 2) && (g->stride_hw == 0 || g->stride_hw == 1 || g->stride_hw == 2),
+             "ea_conv3d_causal: strides are 1 or 2");
+  if (g->stride_t == 2 || g->stride_hw == 2) {
+    EA_REQUIRE(!g->residual && !g->dup_frames && !g->out_planar, "ea_conv3d_causal: a strided convolution takes no residual / frame "
+               "duplication / planar output");
+    EA_REQUIRE(g->stride_hw != 2 || (g->H >= 2 && g->W >= 2), "ea_conv3d_causal: frame too small for stride 2");
+  }
+  const int64_t Ho = g->stride_hw == 2 ? g->H / 2 : g->H, Wo = g->stride_hw == 2 ? g->W / 2 : g->W;
+  const int64_t To = g->stride_t == 2 ? (g->T + 1) / 2 : g->T;
   // 256-pixel CTA tiles against a <=128-wide weight tile (TMEM: 2 stages x 2 sub-tiles x 128 columns) unless the
   // frame is too small to fill the SMs with them.
-  const int64_t tiles256 = g->T * ((g->H + 15) / 16) * ((g->W + 15) / 16) * ((g->Cout_pad + 127) / 128);
+  const int64_t tiles256 = To * ((Ho + 15) / 16) * ((Wo + 15) / 16) * ((g->Cout_pad + 127) / 128);
   const bool big = tiles256 >= 2 * sm_count() && !(g->variant & 1);
   // CTA pairs (variant bit1 disables them: A/B measurements) once there are at least four waves of pair tiles
   const bool pairs = big && !(g->variant & 2) && tiles256 >= 8 * sm_count();

@@ -18,8 +18,10 @@ int check_launch(const char* what);
 
 // 2-D..5-D bf16 tiled tensor map. dims[0] is the contiguous dimension. strides_bytes has rank-1 entries
 // (stride of dims[1..]). swizzle128: box inner extent must be 64 bf16 (128 B).
+// elem_strides (optional, rank entries): traversal stride per dimension (the box then spans box[i] ELEMENTS OF THE TENSOR and
+// ceil(box[i] / elem_strides[i]) of them are loaded).
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box, bool swizzle128);
+                   const uint32_t* box, bool swizzle128, const uint32_t* elem_strides = nullptr);
 
 int sm_count();  // of the CURRENT device (cached per device)
 int current_device();

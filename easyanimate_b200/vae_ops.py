@@ -15,19 +15,23 @@ CONV_VARIANT = int(os.environ.get("EA_CONV_VARIANT", "0"), 0)  # bit0: force 128
 
 
 def conv3d_causal(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, cout: int, *,
-                  residual: Optional[torch.Tensor] = None, dup_frames: bool = False, out_planar: bool = False) -> torch.Tensor:
-    """x [T,H,W,Cin] -> [T',H,W,cout] (or planar [cout,T',H,W]); w_packed [Cout_pad, 27*Cin] from pack_conv_weight."""
+                  residual: Optional[torch.Tensor] = None, dup_frames: bool = False, out_planar: bool = False,
+                  stride_t: int = 1, stride_hw: int = 1) -> torch.Tensor:
+    """x [T,H,W,Cin] -> [T',H',W',cout] (or planar [cout,T',H,W]); w_packed [Cout_pad, 27*Cin] from pack_conv_weight.
+    stride_hw / stride_t = 2: the encoder's down-sampling convolutions (include/ea_b200.h ea_conv3d_args.stride_*)."""
     _req(x, name="x"); _req(w_packed, name="w")
     T, H, W, Cin = x.shape
     assert x.is_contiguous() and w_packed.is_contiguous() and w_packed.shape[1] == 27 * Cin, (x.shape, w_packed.shape)
-    T_out = 2 * T - 1 if dup_frames else T
+    T_out = 2 * T - 1 if dup_frames else ((T + 1) // 2 if stride_t == 2 else T)
+    if stride_hw == 2:
+        H, W = H // 2, W // 2
     shape = (cout, T_out, H, W) if out_planar else (T_out, H, W, cout)
     out = torch.empty(shape, device=x.device, dtype=bf16)
     if residual is not None:
         assert residual.shape == (T, H, W, cout) and residual.is_contiguous()
-    args = L.ConvArgs(x=_p(x), w=_p(w_packed), bias=_p(bias), residual=_p(residual), out=_p(out), T=T, H=H, W=W,
+    args = L.ConvArgs(x=_p(x), w=_p(w_packed), bias=_p(bias), residual=_p(residual), out=_p(out), T=T, H=x.shape[1], W=x.shape[2],
                       Cin=Cin, Cout=cout, Cout_pad=w_packed.shape[0], dup_frames=int(dup_frames),
-                      out_planar=int(out_planar), variant=CONV_VARIANT)
+                      out_planar=int(out_planar), variant=CONV_VARIANT, stride_t=stride_t, stride_hw=stride_hw)
     L.check(L.ea_conv3d_causal(C.byref(args), _stream()), "ea_conv3d_causal")
     return out
 

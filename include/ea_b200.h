@@ -220,6 +220,11 @@ typedef struct {
   int32_t dup_frames;
   int32_t out_planar;
   int32_t variant;      /* 0 = default tiling; bit0: force 128-pixel CTA tiles, bit1: no CTA pairs (A/B measurements) */
+  /* Encoder down-sampling convolutions (downsamplers.py:24-96: F.pad(x, (0,1,0,1)) then CausalConv3d(stride=(s_t,2,2),
+   * padding 0)): stride_hw = 2 -> out[t,i,j] reads input rows 2i..2i+2 / columns 2j..2j+2 (zeros past the bottom / right
+   * edge), out is [T', H/2, W/2, Cout]; stride_t = 2 -> out frame t reads input frames 2t-2..2t (clamped at 0), T' = (T+1)/2.
+   * 0 or 1 = unit stride.  Strided calls take no residual / dup_frames / out_planar. */
+  int32_t stride_t, stride_hw;
 } ea_conv3d_args;
 
 int ea_conv3d_causal(const ea_conv3d_args* args, void* stream);

@@ -156,12 +156,16 @@ def install(monkeypatch):
 # -----------------------------------------------------------------------------------------------------------------------
 # VAE entry points (easyanimate_b200.vae_ops): channels-last [T,H,W,C] activations for one batch element
 # -----------------------------------------------------------------------------------------------------------------------
-def conv3d_causal(x, w_packed, bias, cout, *, residual=None, dup_frames=False, out_planar=False):
+def conv3d_causal(x, w_packed, bias, cout, *, residual=None, dup_frames=False, out_planar=False, stride_t=1, stride_hw=1):
     T, H, W, Cin = x.shape
     w = w_packed.float().view(w_packed.shape[0], 3, 3, 3, Cin).permute(0, 4, 1, 2, 3)[:cout]  # [cout,Cin,kt,kh,kw]
     xin = x.float().permute(3, 0, 1, 2)[None]  # [1,Cin,T,H,W]
     xin = torch.nn.functional.pad(xin, (0, 0, 0, 0, 2, 0), mode="replicate")
-    y = torch.nn.functional.conv3d(xin, w, bias.float()[:cout], padding=(0, 1, 1))[0]  # [cout,T,H,W]
+    if stride_hw == 2:  # downsamplers.py:24-96: zero pad right / bottom by one, no padding inside the convolution
+        xin = torch.nn.functional.pad(xin, (0, 1, 0, 1))
+        y = torch.nn.functional.conv3d(xin, w, bias.float()[:cout], stride=(stride_t, 2, 2))[0]
+    else:
+        y = torch.nn.functional.conv3d(xin, w, bias.float()[:cout], padding=(0, 1, 1), stride=(stride_t, 1, 1))[0]  # [cout,T,H,W]
     y = _r(y)
     if residual is not None:
         y = _r(y + residual.float().permute(3, 0, 1, 2))

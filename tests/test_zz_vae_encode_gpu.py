@@ -34,6 +34,30 @@ def test_strided_convolution_as_stride1_plus_pick():
         torch.testing.assert_close(got.float(), ref, rtol=2 ** -7, atol=2e-2)
 
 
+@pytest.mark.parametrize("T,H,W,Cin,Cout,st", [(5, 18, 22, 64, 64, 2), (5, 18, 22, 64, 64, 1), (9, 33, 47, 128, 128, 2), (1, 16, 16, 64, 128, 1),
+                                              # large enough for the 256-pixel CTA tiles and for CTA pairs
+                                              (5, 256, 320, 128, 128, 2), (3, 416, 512, 128, 256, 1)])
+def test_strided_convolution_kernel(T, H, W, Cin, Cout, st):
+    """ea_conv3d_causal with stride (st, 2, 2) (TMA element strides) against F.conv3d on the reference's padding recipe
+    (downsamplers.py:24-96), and bit for bit against the stride-1 kernel + strided pick."""
+    import torch.nn.functional as F
+    from easyanimate_b200 import vae_ops
+    g = torch.Generator(device="cuda").manual_seed(T * H + W)
+    x = torch.randn((T, H, W, Cin), device="cuda", generator=g).to(bf16)
+    w = (torch.randn((Cout, Cin, 3, 3, 3), device="cuda", generator=g) * (27 * Cin) ** -0.5).to(bf16)
+    b = (torch.randn((Cout,), device="cuda", generator=g) * 0.1).to(bf16)
+    wp = vae_ops.pack_conv_weight(w)
+    got = vae_ops.conv3d_causal(x, wp, b, Cout, stride_t=st, stride_hw=2)
+    xin = x.float().permute(3, 0, 1, 2)[None]
+    xin = F.pad(F.pad(xin, (0, 1, 0, 1)), (0, 0, 0, 0, 2, 0), mode="replicate")
+    ref = F.conv3d(xin, w.float(), b.float(), stride=(st, 2, 2))[0].permute(1, 2, 3, 0)
+    assert got.shape == ref.shape == ((T + 1) // 2 if st == 2 else T, H // 2, W // 2, Cout)
+    torch.testing.assert_close(got.float(), ref, rtol=2 ** -7, atol=2e-2)
+    full = vae_ops.conv3d_causal(x, wp, b, Cout)
+    pick = (full[::2] if st == 2 else full)[:, 1::2, 1::2]
+    assert torch.equal(got, pick[:, :H // 2, :W // 2])  # same taps, same k order, same accumulator: identical
+
+
 def prelude_encode_golden():
     """The part of test_vae_encode_matches_reference_golden that needs no GPU (run on CPU by tests/test_gpu_preludes_cpu.py)."""
     from safetensors import safe_open

@@ -6,6 +6,7 @@ tail -5 gpurun_out/r02_pytest1.log
 python bench.py --steps 3 --warmup 3 > gpurun_out/r02_bench1.json 2> gpurun_out/r02_bench1.err; echo "bench rc=$?"
 tail -c 600 gpurun_out/r02_bench1.err
 python tools/bench_kernels.py attn > gpurun_out/r02_attn_base.log 2>&1
+for v in 0x210c 0x211c 0x290c; do EA_ATTN_VARIANT=$v EA_ATTN_NO_COMPARE=1 python tools/bench_kernels.py attn >> gpurun_out/r02_attn_3x64.log 2>&1; done
 python tools/bench_kernels.py gemm > gpurun_out/r02_gemm_base.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/r02_launches_step.csv \
     python bench.py --steps 1 --warmup 3 --no-vae --no-secondary --no-cpu-baseline > gpurun_out/r02_launches_step.out 2>&1
