@@ -46,6 +46,18 @@ class GemmArgs(C.Structure):
     ]
 
 
+MAX_PEERS = 8
+
+
+class QkvPeers(C.Structure):
+    _fields_ = [("q", vp * MAX_PEERS), ("k", vp * MAX_PEERS), ("v", vp * MAX_PEERS), ("heads_per_peer", i64)]
+
+
+class AttnPeers(C.Structure):
+    _fields_ = [("out_video", vp * MAX_PEERS), ("out_text", vp * MAX_PEERS), ("n_peers", i64), ("tokens_per_peer", i64),
+                ("out_heads", i64), ("head0", i64)]
+
+
 class QkvArgs(C.Structure):
     _fields_ = [
         ("a", vp), ("w", vp), ("bias", vp),
@@ -54,7 +66,7 @@ class QkvArgs(C.Structure):
         ("q", vp), ("k", vp), ("v", vp),
         ("M", i64), ("d", i64), ("lda", i64),
         ("rows_per_batch", i64), ("S", i64), ("seq_offset", i64),
-        ("ln_eps", f32),
+        ("ln_eps", f32), ("peers", C.POINTER(QkvPeers)),
     ]
 
 
@@ -85,7 +97,7 @@ class AttnArgs(C.Structure):
         ("q", vp), ("k", vp), ("v", vp),
         ("out_text", vp), ("out_video", vp),
         ("B", i64), ("H", i64), ("S", i64), ("S_text", i64), ("S_pad", i64), ("head_dim", i64),
-        ("scale", f32), ("variant", i32),
+        ("scale", f32), ("variant", i32), ("peers", C.POINTER(AttnPeers)),
     ]
 
 
@@ -117,6 +129,7 @@ ea_patchify = _sig("ea_patchify", [vp, vp, vp, i64, i64, i64, i64, i64, i64, i64
 ea_unpatchify = _sig("ea_unpatchify", [vp, vp, i64, i64, i64, i64, i64, i64, vp])
 ea_attn_fwd = _sig("ea_attn_fwd", [C.POINTER(AttnArgs), vp])
 ea_attn_generations = _sig("ea_attn_generations", [])
+ea_enable_peer_access = _sig("ea_enable_peer_access", [i32])
 ea_cfg_euler_step = _sig("ea_cfg_euler_step", [vp, vp, vp, vp, i64, f32, i32, f32, f32, vp])
 ea_l1_sums = _sig("ea_l1_sums", [vp, vp, vp, i64, vp])
 ea_ew_addsub = _sig("ea_ew_addsub", [vp, vp, vp, i64, i32, vp])

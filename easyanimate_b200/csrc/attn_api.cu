@@ -27,8 +27,9 @@ extern "C" int ea_attn_fwd(const ea_attn_args* g, void* stream_) {
   EA_REQUIRE(g->B > 0 && g->H > 0 && g->S > 0, "ea_attn_fwd: empty problem");
   EA_REQUIRE(g->head_dim == 64, "ea_attn_fwd: head_dim must be 64");
   EA_REQUIRE(g->S_text >= 0 && g->S_text <= g->S, "ea_attn_fwd: bad S_text");
-  EA_REQUIRE(g->S_text == 0 || g->out_text, "ea_attn_fwd: out_text missing");
-  EA_REQUIRE(g->S_text == g->S || g->out_video, "ea_attn_fwd: out_video missing");
+  EA_REQUIRE(g->peers || g->S_text == 0 || g->out_text, "ea_attn_fwd: out_text missing");
+  EA_REQUIRE(g->peers || g->S_text == g->S || g->out_video, "ea_attn_fwd: out_video missing");
+  EA_REQUIRE(!g->peers || (g->variant & 0x1100) == 0x100, "ea_attn_fwd: peer outputs exist for the sixth-generation kernel only");
   EA_REQUIRE(g->B * g->H <= 65535, "ea_attn_fwd: B*H exceeds grid.y");
   if ((g->variant & 0x1100) == 0x100) return ea::launch_attn6(g, (g->variant >> 4) & 7, stream);
 #ifdef EA_ATTN_AB

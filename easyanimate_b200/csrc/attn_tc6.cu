@@ -40,6 +40,11 @@ struct Args {
   int B, H, S, S_text;
   float scale_log2;
   uint32_t dep_zero;  // always 0; a value the compiler cannot see through (exp_row_phased)
+  // sequence parallelism (ea_attn_peers): this GPU computed heads [head0, head0 + H) of out_heads for ALL tokens; a video
+  // token's row goes to the GPU that owns the token (tokens_per_peer each), the text rows to every GPU.  n_peers = 0: local.
+  int n_peers, tokens_per_peer, out_heads, head0;
+  bf16* out_video_peers[EA_MAX_PEERS];
+  bf16* out_text_peers[EA_MAX_PEERS];
 };
 
 // NT query tiles of 128 rows per CTA, key blocks of KT keys.  (2, 128): the layout described above.  (3, 64): three softmax
@@ -488,13 +493,31 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     const float inv_l = (TRUNC ? 1.00282f : 1.0f) / l;
     const int srow = q0 + t * kQT + r;
     bf16* dst = nullptr;
+    int ndst = 1;            // text rows under sequence parallelism are delivered to every GPU of the group
+    int64_t text_off = 0;
     if (srow < p.S) {
       const int bb = bh / p.H, h = bh % p.H;
-      const int64_t d = (int64_t)p.H * kHD;
-      if (srow < p.S_text)
-        dst = p.out_text + ((int64_t)bb * p.S_text + srow) * d + h * kHD;
-      else
-        dst = p.out_video + ((int64_t)bb * (p.S - p.S_text) + (srow - p.S_text)) * d + h * kHD;
+      if (p.n_peers == 0) {
+        const int64_t d = (int64_t)p.H * kHD;
+        if (srow < p.S_text)
+          dst = p.out_text + ((int64_t)bb * p.S_text + srow) * d + h * kHD;
+        else
+          dst = p.out_video + ((int64_t)bb * (p.S - p.S_text) + (srow - p.S_text)) * d + h * kHD;
+      } else {
+        // Ulysses return exchange fused into the epilogue: [token, head] rows of 128 bytes stored straight into the
+        // token-major [B, tokens, out_heads * 64] buffer of the GPU that owns the token (NVLink when it is a peer)
+        const int64_t d = (int64_t)p.out_heads * kHD;
+        if (srow < p.S_text) {
+          text_off = ((int64_t)bb * p.S_text + srow) * d + (int64_t)(p.head0 + h) * kHD;
+          dst = p.out_text_peers[0] + text_off;
+          ndst = p.n_peers;
+        } else {
+          const int v = srow - p.S_text;
+          const int owner = v / p.tokens_per_peer;
+          dst = p.out_video_peers[owner] + ((int64_t)bb * p.tokens_per_peer + (v - owner * p.tokens_per_peer)) * d +
+                (int64_t)(p.head0 + h) * kHD;
+        }
+      }
     }
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
@@ -511,6 +534,7 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
           w.z = pack_bf16x2(__uint_as_float(v[i * 8 + 4]) * inv_l, __uint_as_float(v[i * 8 + 5]) * inv_l);
           w.w = pack_bf16x2(__uint_as_float(v[i * 8 + 6]) * inv_l, __uint_as_float(v[i * 8 + 7]) * inv_l);
           *reinterpret_cast<uint4*>(dst + c * 32 + i * 8) = w;
+          for (int pr = 1; pr < ndst; ++pr) *reinterpret_cast<uint4*>(p.out_text_peers[pr] + text_off + c * 32 + i * 8) = w;
         }
       }
     }
@@ -546,6 +570,18 @@ static int launch(const ea_attn_args* g, cudaStream_t stream) {
   p.B = (int)g->B; p.H = (int)g->H; p.S = (int)g->S; p.S_text = (int)g->S_text;
   p.scale_log2 = g->scale * 1.4426950408889634f;
   p.dep_zero = 0;
+  if (g->peers != nullptr) {
+    const ea_attn_peers* pe = g->peers;
+    if (pe->n_peers < 1 || pe->n_peers > EA_MAX_PEERS || pe->tokens_per_peer <= 0 || pe->out_heads < pe->head0 + g->H ||
+        pe->tokens_per_peer * pe->n_peers != g->S - g->S_text)
+      return fail(EA_ERR_INVALID, "ea_attn_fwd: bad ea_attn_peers (n_peers, tokens_per_peer x n_peers == video tokens, head range)");
+    p.n_peers = (int)pe->n_peers; p.tokens_per_peer = (int)pe->tokens_per_peer; p.out_heads = (int)pe->out_heads; p.head0 = (int)pe->head0;
+    for (int i = 0; i < p.n_peers; ++i) {
+      if (!pe->out_video[i] || (g->S_text > 0 && !pe->out_text[i])) return fail(EA_ERR_INVALID, "ea_attn_fwd: NULL peer output buffer");
+      p.out_video_peers[i] = reinterpret_cast<bf16*>(pe->out_video[i]);
+      p.out_text_peers[i] = reinterpret_cast<bf16*>(pe->out_text[i]);
+    }
+  }
   auto kern = attn6_kernel<POLY, PHASED, TRUNC, NT, KT>;
   static ::ea::PerDeviceFlag attr_flag;
   const int attr_dev = ::ea::current_device();

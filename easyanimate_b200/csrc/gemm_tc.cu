@@ -58,6 +58,12 @@ struct GemmDevArgs {
   int S;
   int seq_offset;
   float ln_eps;
+  // sequence parallelism (ea_qkv_peers): head h is stored on the GPU that owns it, q_peers[h / heads_per_peer] (this GPU's
+  // own buffer or a peer's, mapped over NVLink); 0 = everything goes to q/k/v above
+  int heads_per_peer;
+  bf16* q_peers[EA_MAX_PEERS];
+  bf16* k_peers[EA_MAX_PEERS];
+  bf16* v_peers[EA_MAX_PEERS];
 };
 
 template <int BN>
@@ -268,7 +274,18 @@ EA_DEVICE void epilogue_qkv_head(const GemmDevArgs& p, int row, int col0, uint32
     }
   }
   bf16* base = which == 0 ? p.q : (which == 1 ? p.k : p.v);
-  bf16* o = base + (((int64_t)b * p.heads + head) * p.S + p.seq_offset + s) * 64;
+  int head_l = head, heads_l = p.heads;
+  if (p.heads_per_peer > 0) {
+    // Ulysses exchange fused into the projection: the row goes straight into the q/k/v buffer [B, heads_per_peer, S, 64] of
+    // the GPU that runs attention for this head - a 128-byte store over NVLink when that is a peer (a NULL entry = a head
+    // this call does not have to deliver: the replicated text rows are projected on every GPU for its own heads only)
+    const int owner = head / p.heads_per_peer;
+    base = (which == 0 ? p.q_peers : (which == 1 ? p.k_peers : p.v_peers))[owner];
+    if (base == nullptr) return;
+    head_l = head - owner * p.heads_per_peer;
+    heads_l = p.heads_per_peer;
+  }
+  bf16* o = base + (((int64_t)b * heads_l + head_l) * p.S + p.seq_offset + s) * 64;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     uint4 w;
@@ -695,7 +712,7 @@ extern "C" int ea_gemm(const ea_gemm_args* g, void* stream_) {
 extern "C" int ea_qkv_gemm_ln_rope(const ea_qkv_args* g, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   EA_REQUIRE(g != nullptr, "ea_qkv: null args");
-  EA_REQUIRE(g->a && g->w && g->bias && g->q && g->k && g->v, "ea_qkv: null pointer");
+  EA_REQUIRE(g->a && g->w && g->bias && ((g->q && g->k && g->v) || g->peers), "ea_qkv: null pointer");
   EA_REQUIRE(g->ln_q_w && g->ln_q_b && g->ln_k_w && g->ln_k_b, "ea_qkv: null LayerNorm parameter");
   EA_REQUIRE(g->d > 0 && g->d % 64 == 0, "ea_qkv: d must be a multiple of the head size 64");
   EA_REQUIRE(g->M > 0 && g->rows_per_batch > 0 && g->M % g->rows_per_batch == 0, "ea_qkv: M must be B*rows_per_batch");
@@ -711,6 +728,17 @@ extern "C" int ea_qkv_gemm_ln_rope(const ea_qkv_args* g, void* stream_) {
   p.q = reinterpret_cast<bf16*>(g->q); p.k = reinterpret_cast<bf16*>(g->k); p.v = reinterpret_cast<bf16*>(g->v);
   p.d = (int)g->d; p.heads = (int)(g->d / 64); p.S = (int)g->S; p.seq_offset = (int)g->seq_offset;
   p.rows_per_batch = (int)g->rows_per_batch; p.ln_eps = g->ln_eps;
+  if (g->peers != nullptr) {
+    const ea_qkv_peers* pe = g->peers;
+    EA_REQUIRE(pe->heads_per_peer > 0 && (g->d / 64) % pe->heads_per_peer == 0 && (g->d / 64) / pe->heads_per_peer <= EA_MAX_PEERS,
+               "ea_qkv: heads_per_peer must divide the head count into at most EA_MAX_PEERS groups");
+    p.heads_per_peer = (int)pe->heads_per_peer;
+    for (int i = 0; i < EA_MAX_PEERS; ++i) {
+      p.q_peers[i] = reinterpret_cast<bf16*>(pe->q[i]);
+      p.k_peers[i] = reinterpret_cast<bf16*>(pe->k[i]);
+      p.v_peers[i] = reinterpret_cast<bf16*>(pe->v[i]);
+    }
+  }
   // an N tile must not straddle the q|k|v boundaries: the widest tile that divides d
   if (g->d % 256 == 0 && use_pairs(p)) return launch_gemm2<EPI_QKV>(g->a, g->lda, g->w, g->d, p, stream);
   if (g->d % 256 == 0) return launch_gemm<256, EPI_QKV>(g->a, g->lda, g->w, g->d, p, stream);

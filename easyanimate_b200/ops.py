@@ -73,13 +73,15 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
 def qkv_gemm_ln_rope(a: torch.Tensor, w_qkv: torch.Tensor, b_qkv: torch.Tensor, ln_q: Tuple[torch.Tensor, torch.Tensor],
                      ln_k: Tuple[torch.Tensor, torch.Tensor], rope: Optional[Tuple[torch.Tensor, torch.Tensor]],
                      q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, rows_per_batch: int, seq_offset: int,
-                     eps: float = 1e-6) -> None:
-    """Fused q/k/v projection + per-head LayerNorm + RoPE, written into q/k/v[B,H,S,64] at seq_offset."""
+                     eps: float = 1e-6, peers=None) -> None:
+    """Fused q/k/v projection + per-head LayerNorm + RoPE, written into q/k/v[B,H,S,64] at seq_offset.
+    peers (an _lib.QkvPeers): sequence parallelism - q/k/v are this rank's [B,H/P,S,64] buffers and head h of every row is
+    stored into the buffer of the rank that owns it (include/ea_b200.h ea_qkv_peers)."""
     _req(a, name="a"); _req(w_qkv, name="w_qkv")
     M, d = a.shape
     assert w_qkv.shape == (3 * d, d) and w_qkv.is_contiguous() and b_qkv.shape == (3 * d,)
     B, H, S, hd = q.shape
-    assert hd == 64 and H * 64 == d and k.shape == q.shape and v.shape == q.shape
+    assert hd == 64 and H * 64 == (d if peers is None else peers.heads_per_peer * 64) and k.shape == q.shape and v.shape == q.shape
     assert q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
     cos = sin = None
     if rope is not None:
@@ -89,7 +91,8 @@ def qkv_gemm_ln_rope(a: torch.Tensor, w_qkv: torch.Tensor, b_qkv: torch.Tensor, 
     args = L.QkvArgs(
         a=_p(a), w=_p(w_qkv), bias=_p(b_qkv), ln_q_w=_p(ln_q[0]), ln_q_b=_p(ln_q[1]), ln_k_w=_p(ln_k[0]),
         ln_k_b=_p(ln_k[1]), rope_cos=_p(cos), rope_sin=_p(sin), q=_p(q), k=_p(k), v=_p(v), M=M, d=d, lda=a.stride(0),
-        rows_per_batch=rows_per_batch, S=S, seq_offset=seq_offset, ln_eps=eps)
+        rows_per_batch=rows_per_batch, S=S, seq_offset=seq_offset, ln_eps=eps,
+        peers=None if peers is None else C.pointer(peers))
     L.check(L.ea_qkv_gemm_ln_rope(C.byref(args), _stream()), "ea_qkv_gemm_ln_rope")
 
 
@@ -233,8 +236,10 @@ def ew_add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None,
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, S_text: int, *, scale: Optional[float] = None,
-              variant: int = ATTN_VARIANT) -> Tuple[torch.Tensor, torch.Tensor]:
-    """softmax(q k^T * scale) v for q,k,v [B,H,S,64]; returns (out_text [B,S_text,H*64], out_video [B,S-S_text,H*64])."""
+              variant: int = ATTN_VARIANT, peers=None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """softmax(q k^T * scale) v for q,k,v [B,H,S,64]; returns (out_text [B,S_text,H*64], out_video [B,S-S_text,H*64]).
+    peers (an _lib.AttnPeers): sequence parallelism - the rows are stored into the owning ranks' buffers instead
+    (include/ea_b200.h ea_attn_peers) and (None, None) is returned."""
     _req(q, name="q"); _req(k, name="k"); _req(v, name="v")
     B, H, S, hd = q.shape
     assert hd == 64 and k.shape == q.shape and q.is_contiguous() and k.is_contiguous()
@@ -250,11 +255,13 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, S_text: int, *,
         v = vt
     else:
         assert v.shape == q.shape and v.is_contiguous()
-    out_text = torch.empty((B, S_text, H * 64), device=q.device, dtype=bf16)
-    out_video = torch.empty((B, S - S_text, H * 64), device=q.device, dtype=bf16)
-    args = L.AttnArgs(q=_p(q), k=_p(k), v=_p(v), out_text=_p(out_text) if S_text else None,
-                      out_video=_p(out_video) if S - S_text else None, B=B, H=H, S=S, S_text=S_text, S_pad=S_pad,
-                      head_dim=64, scale=scale, variant=variant)
+    out_text = out_video = None
+    if peers is None:
+        out_text = torch.empty((B, S_text, H * 64), device=q.device, dtype=bf16)
+        out_video = torch.empty((B, S - S_text, H * 64), device=q.device, dtype=bf16)
+    args = L.AttnArgs(q=_p(q), k=_p(k), v=_p(v), out_text=_p(out_text) if (S_text and peers is None) else None,
+                      out_video=_p(out_video) if (S - S_text and peers is None) else None, B=B, H=H, S=S, S_text=S_text,
+                      S_pad=S_pad, head_dim=64, scale=scale, variant=variant, peers=None if peers is None else C.pointer(peers))
     timing = ATTN_TIMING
     if timing is not None:  # bench.py: per-launch CUDA events on the launching stream for the roofline line
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

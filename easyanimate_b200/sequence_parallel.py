@@ -1,19 +1,26 @@
-"""Ulysses sequence parallelism for ONE video across the ranks of a group.  The reference has no multi-GPU inference code at
-this commit (no xfuser / ulysses / ring); joint text+video attention (processor.py:287-289) makes a
+"""Sequence parallelism for ONE video across the ranks of a group.  The reference has no multi-GPU inference code at this
+commit (no xfuser / ulysses / ring); joint text+video attention (processor.py:287-289) makes a
 per-block exchange unavoidable once one video spans more than the two CFG branches, and this module
-is this framework's own design for it: every rank owns a contiguous slice of the video tokens for the
+is this framework's own design for it (Ulysses-style): every rank owns a contiguous slice of the video tokens for the
 per-token work (AdaLN, projections, feed-forward) and, inside attention, all tokens of a slice of the HEADS.  The text
-tokens are few (256) and replicated.  Two exchanges per block, both plain NCCL collectives here:
+tokens are few (256) and replicated.
 
-    q/k/v  [B, H, S_t + S_loc, 64]  --all_to_all-->  [B, H/P, S_t + S_v, 64]      (before attention)
-    out    [B, S_v, (H/P)*64]       --all_to_all-->  [B, S_loc, H*64]  (+ all_gather of the text rows)
+Two implementations of the two exchanges per block:
 
-STATUS: the exchange logic is covered by a world_size-2 gloo test against single-process attention
-(tests/test_dist_sp_cpu.py, which also runs the whole forward, a TeaCache sequence and the 2 CFG branches x 2 ranks sampler
-topology with CPU stand-ins for the kernels); the model integration (`EasyAnimateTransformer3DModel.set_sequence_parallel_group`) has NOT run
-on GPUs yet - tools/test_multigpu.py checks it against the single-GPU forward and is the first thing to run next round.
-The B200-native form of these exchanges (P2P stores from the QKV-GEMM / attention epilogues into the peers' buffers) is
-DESIGN.md section 8, item 3; this NCCL version is the baseline it will be measured against.
+* `PeerExchange` (the product path on NVLink-connected GPUs, `mode="p2p"`): NO separate exchange pass.  The q/k/v buffers
+  [B, H/P, S, 64] and the attention-output buffers of every rank are mapped into every other rank (CUDA IPC); the QKV
+  projection's epilogue stores head h of its rows straight into the buffer of the rank that owns h, and the attention
+  epilogue stores each token's row straight into the token-major buffer of the rank that owns the token
+  (include/ea_b200.h `ea_qkv_peers` / `ea_attn_peers`: 128-byte NVLink stores issued from the same kernels as the tcgen05
+  tiles).  The only collectives left are two 4-byte all-reduces per block that order the kernels of different GPUs.
+* NCCL collectives (`mode="nccl"`, also what the gloo CPU tests run): two `all_to_all_single` + one `all_gather` per block
+  plus the permute copies around them - the baseline the fused path is measured against.
+
+    q/k/v  [B, H, S_t + S_loc, 64]  --exchange-->  [B, H/P, S_t + S_v, 64]      (before attention)
+    out    [B, S_v, (H/P)*64]       --exchange-->  [B, S_loc, H*64]  (+ the text rows on every rank)
+
+Host logic of the collective form is covered by world_size-2/4 gloo tests against single-process attention / forward /
+sampler (tests/test_dist_sp_cpu.py); both forms are checked on GPUs against the single-GPU forward by tools/test_multigpu.py.
 """
 from __future__ import annotations
 
@@ -36,12 +43,78 @@ def all_reduce_floats(values, group) -> list:
     return [float(v) for v in t.cpu()]
 
 
+class PeerExchange:
+    """Symmetric q/k/v and attention-output buffers of one (B, H, S_t, S_loc) problem, mapped into every rank of the group,
+    and the pointer tables the fused kernels take.  Built once per shape and reused by every block of every step."""
+
+    def __init__(self, group, B: int, H: int, S_t: int, S_loc: int, device):
+        from . import _lib as L
+        self.group, self.rank, self.world = group, dist.get_rank(group), dist.get_world_size(group)
+        P = self.world
+        if P > L.MAX_PEERS:
+            raise ValueError(f"peer exchange supports up to {L.MAX_PEERS} ranks per group")
+        if H % P:
+            raise ValueError(f"sequence parallelism needs the head count ({H}) to divide by the group size ({P})")
+        self.B, self.H, self.Hl, self.S_t, self.S_loc = B, H, H // P, S_t, S_loc
+        S = S_t + P * S_loc
+        bf16 = torch.bfloat16
+        # one allocation per buffer (a CUDA IPC handle names a whole allocation + offset; torch's storage sharing does both)
+        self.q = torch.empty((B, self.Hl, S, 64), device=device, dtype=bf16)
+        self.k = torch.empty_like(self.q)
+        self.v = torch.empty_like(self.q)
+        self.out_video = torch.empty((B, S_loc, H * 64), device=device, dtype=bf16)
+        self.out_text = torch.empty((B, S_t, H * 64), device=device, dtype=bf16)
+        self._flag = torch.zeros((1,), device=device, dtype=torch.int32)
+        mine = [self.q, self.k, self.v, self.out_video, self.out_text]
+        handles = [t.untyped_storage()._share_cuda_() + (t.storage_offset() * t.element_size(),) for t in mine]
+        gathered = [None] * P
+        dist.all_gather_object(gathered, (torch.cuda.current_device(), handles), group=group)
+        self._peer_storages = []  # keep the mappings alive
+        ptrs = []
+        for r, (peer_dev, hs) in enumerate(gathered):
+            if r == self.rank:
+                ptrs.append([t.data_ptr() for t in mine])
+                continue
+            L.check(L.ea_enable_peer_access(int(peer_dev)), "ea_enable_peer_access")
+            row = []
+            for h in hs:
+                st = torch.UntypedStorage._new_shared_cuda(*h[:8])
+                self._peer_storages.append(st)
+                row.append(st.data_ptr() + h[8])
+            ptrs.append(row)
+        self.qkv_video, self.qkv_text, self.attn = L.QkvPeers(), L.QkvPeers(), L.AttnPeers()
+        self.qkv_video.heads_per_peer = self.qkv_text.heads_per_peer = self.Hl
+        for r in range(P):
+            self.qkv_video.q[r], self.qkv_video.k[r], self.qkv_video.v[r] = ptrs[r][0], ptrs[r][1], ptrs[r][2]
+            self.attn.out_video[r], self.attn.out_text[r] = ptrs[r][3], ptrs[r][4]
+        # text rows are replicated: every rank projects them itself and keeps its own heads only
+        self.qkv_text.q[self.rank], self.qkv_text.k[self.rank], self.qkv_text.v[self.rank] = ptrs[self.rank][:3]
+        self.attn.n_peers, self.attn.tokens_per_peer, self.attn.out_heads, self.attn.head0 = P, S_loc, H, self.rank * self.Hl
+        dist.barrier(group=group)  # nobody stores into a peer before every mapping exists
+
+    def barrier(self):
+        """Orders the kernels of different GPUs on the compute stream (no host synchronisation): the 4-byte all-reduce can
+        only complete on a rank once every rank has launched it, i.e. once every rank's preceding kernel has finished."""
+        dist.all_reduce(self._flag, group=self.group)
+
+
 class UlyssesAttention:
-    def __init__(self, group, attention_fn: Optional[Callable] = None):
+    def __init__(self, group, attention_fn: Optional[Callable] = None, mode: Optional[str] = None):
+        import os
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self._attention = attention_fn  # (q, k, v, S_t) -> (out_text [B,S_t,h*64], out_video [B,S-S_t,h*64]); default ops.attention
+        mode = mode or os.environ.get("EA_SP_MODE", "p2p")
+        # the fused peer-store exchange needs CUDA IPC between the ranks' GPUs; gloo (CPU tests) runs the collective form
+        self.p2p = mode == "p2p" and dist.get_backend(group) == "nccl" and attention_fn is None
+        self._px = {}
+
+    def exchange(self, B: int, H: int, S_t: int, S_loc: int, device) -> PeerExchange:
+        key = (B, H, S_t, S_loc, str(device))
+        if key not in self._px:
+            self._px = {key: PeerExchange(self.group, B, H, S_t, S_loc, device)}  # one shape at a time: free the previous buffers
+        return self._px[key]
 
     # ---- token sharding of the per-token streams ----------------------------------------------------------------
     def local_range(self, S_v: int) -> Tuple[int, int]:

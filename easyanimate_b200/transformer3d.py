@@ -121,13 +121,28 @@ class EasyAnimateDiTBlock(nn.Module):
         n_t = self._ln_mod(x_t, self.norm1, mod, 3, S_t, out=ws.n_t)
         a_t = self.attn2 if self.attn2 is not None else self.attn1
         w1, b1 = self.attn1.fused_qkv()
-        ops.qkv_gemm_ln_rope(n_v, w1, b1, (self.attn1.norm_q.weight, self.attn1.norm_q.bias),
-                             (self.attn1.norm_k.weight, self.attn1.norm_k.bias), rope, ws.q, ws.k, ws.v,
-                             rows_per_batch=S_v, seq_offset=S_t, eps=self.attn1.norm_q.eps)
         w2, b2 = a_t.fused_qkv()
-        ops.qkv_gemm_ln_rope(n_t, w2, b2, (a_t.norm_q.weight, a_t.norm_q.bias), (a_t.norm_k.weight, a_t.norm_k.bias),
-                             None, ws.q, ws.k, ws.v, rows_per_batch=S_t, seq_offset=0, eps=a_t.norm_q.eps)
-        o_t, o_v = ops.attention(ws.q, ws.k, ws.v, S_t) if ws.sp is None else ws.sp.attention(ws.q, ws.k, ws.v, S_t)
+        ln1 = ((self.attn1.norm_q.weight, self.attn1.norm_q.bias), (self.attn1.norm_k.weight, self.attn1.norm_k.bias))
+        ln2 = ((a_t.norm_q.weight, a_t.norm_q.bias), (a_t.norm_k.weight, a_t.norm_k.bias))
+        if ws.px is not None:
+            # sequence parallelism, fused exchange (sequence_parallel.PeerExchange): the projections store each head's rows
+            # into the q/k/v buffer of the rank that owns the head, attention stores each token's row into the buffer of the
+            # rank that owns the token; two 4-byte all-reduces order the kernels across GPUs
+            px = ws.px
+            ops.qkv_gemm_ln_rope(n_v, w1, b1, ln1[0], ln1[1], rope, px.q, px.k, px.v, rows_per_batch=S_v,
+                                 seq_offset=S_t + px.rank * S_v, eps=self.attn1.norm_q.eps, peers=px.qkv_video)
+            ops.qkv_gemm_ln_rope(n_t, w2, b2, ln2[0], ln2[1], None, px.q, px.k, px.v, rows_per_batch=S_t, seq_offset=0,
+                                 eps=a_t.norm_q.eps, peers=px.qkv_text)
+            px.barrier()
+            ops.attention(px.q, px.k, px.v, S_t, peers=px.attn)
+            px.barrier()
+            o_t, o_v = px.out_text, px.out_video
+        else:
+            ops.qkv_gemm_ln_rope(n_v, w1, b1, ln1[0], ln1[1], rope, ws.q, ws.k, ws.v, rows_per_batch=S_v, seq_offset=S_t,
+                                 eps=self.attn1.norm_q.eps)
+            ops.qkv_gemm_ln_rope(n_t, w2, b2, ln2[0], ln2[1], None, ws.q, ws.k, ws.v, rows_per_batch=S_t, seq_offset=0,
+                                 eps=a_t.norm_q.eps)
+            o_t, o_v = ops.attention(ws.q, ws.k, ws.v, S_t) if ws.sp is None else ws.sp.attention(ws.q, ws.k, ws.v, S_t)
         ops.gemm(o_v.view(B * S_v, d), self.attn1.to_out[0].weight, self.attn1.to_out[0].bias,
                  epilogue=L.EPI_BIAS_GATE_RES, residual=x_v, gate=mod[:, 2 * d:3 * d], rows_per_batch=S_v, out=x_v)
         ops.gemm(o_t.view(B * S_t, d), a_t.to_out[0].weight, a_t.to_out[0].bias,
@@ -196,7 +211,9 @@ class _Workspace:
         S = S_v + S_t
         e = lambda *shape: torch.empty(shape, device=device, dtype=bf16)  # noqa: E731
         self.n_v, self.n_t = e(B * S_v, d), e(B * S_t, d)
-        self.q, self.k, self.v = e(B, heads, S, 64), e(B, heads, S, 64), e(B, heads, S, 64)
+        self.px = sp.exchange(B, heads, S_t, S_v, device) if (sp is not None and sp.p2p) else None
+        if self.px is None:
+            self.q, self.k, self.v = e(B, heads, S, 64), e(B, heads, S, 64), e(B, heads, S, 64)
         self.h_v, self.h_t = e(B * S_v, ff_inner), e(B * S_t, ff_inner)
 
 

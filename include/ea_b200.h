@@ -75,6 +75,21 @@ int ea_gemm(const ea_gemm_args* args, void* stream);
  * 3-D RoPE on q,k for video rows, written head-major into q/k/v[B,H,S,64] at sequence offset seq_offset.
  * Replaces processor.py:244-285 (to_q/to_k/to_v, view/transpose, norm_q/norm_k, cat, apply_rotary_emb).
  * M = B * rows_per_batch (rows_per_batch = S_text or S_video). d = H*64. */
+/* Sequence parallelism for ONE video over up to EA_MAX_PEERS GPUs of a node (no counterpart in the reference, which has
+ * no multi-GPU inference path): the two exchanges joint attention needs per block (processor.py:287-289
+ * sees every token of every head) are FUSED into the kernels on either side of it.  Each GPU projects q/k/v for its slice
+ * of the video tokens and all heads; head h of those rows is stored by the projection's epilogue directly into the q/k/v
+ * buffer [B, heads_per_peer, S, 64] of the GPU that owns head h (entry h / heads_per_peer: this GPU's own buffer or a
+ * peer's buffer mapped through CUDA IPC - the store then travels over NVLink).  NULL entries are skipped (the replicated
+ * text rows are projected on every GPU for its own heads only). */
+#define EA_MAX_PEERS 8
+typedef struct {
+  void* q[EA_MAX_PEERS];
+  void* k[EA_MAX_PEERS];
+  void* v[EA_MAX_PEERS];
+  int64_t heads_per_peer;
+} ea_qkv_peers;
+
 typedef struct {
   const void* a;          /* [M,d] bf16, row stride lda */
   const void* w;          /* [3d,d] bf16: rows [0,d)=to_q, [d,2d)=to_k, [2d,3d)=to_v */
@@ -93,6 +108,7 @@ typedef struct {
   int64_t S;              /* total sequence length of q/k/v */
   int64_t seq_offset;     /* where this part's rows start inside S */
   float ln_eps;
+  const ea_qkv_peers* peers; /* NULL: q/k/v above hold all d/64 heads; else see ea_qkv_peers (q/k/v are then ignored) */
 } ea_qkv_args;
 
 int ea_qkv_gemm_ln_rope(const ea_qkv_args* args, void* stream);
@@ -184,6 +200,16 @@ int ea_ew_addsub(const void* a, const void* b, void* out, int64_t n, int32_t sub
  *   Other values select retired generations (first: bits 0-1, fourth: 0x0c|poly<<4, ninth: 0x1000|...), present only in an
  *   A/B build (EA_ATTN_AB=1 build.sh; tools/attn_ab/); ea_attn_generations() returns the bitmask of generations built
  *   in (bit 6 always).  Anything else is EA_ERR_INVALID. */
+/* The return half of the exchange, fused into the attention epilogue: this GPU ran attention for heads
+ * [head0, head0 + H) of out_heads over ALL S tokens; the row of video token v goes into out_video[v / tokens_per_peer]
+ * (the token-major [B, tokens_per_peer, out_heads*64] buffer of the GPU that owns the token), text rows into the
+ * [B, S_text, out_heads*64] buffer of EVERY GPU (the text stream is replicated). */
+typedef struct {
+  void* out_video[EA_MAX_PEERS];
+  void* out_text[EA_MAX_PEERS];
+  int64_t n_peers, tokens_per_peer, out_heads, head0;
+} ea_attn_peers;
+
 typedef struct {
   const void* q;
   const void* k;
@@ -193,10 +219,15 @@ typedef struct {
   int64_t B, H, S, S_text, S_pad, head_dim;
   float scale;
   int32_t variant;
+  const ea_attn_peers* peers; /* NULL: out_text / out_video above; else see ea_attn_peers (they are then ignored) */
 } ea_attn_args;
 
 int ea_attn_fwd(const ea_attn_args* args, void* stream);
 int ea_attn_generations(void);
+
+/* cudaDeviceEnablePeerAccess(peer_device) from the current device (idempotent): kernels of this library on the current
+ * device may then dereference pointers into `peer_device`'s memory (ea_qkv_peers / ea_attn_peers buffers). */
+int ea_enable_peer_access(int32_t peer_device);
 
 /* ------------------------------------------------------------------------------------------------------------
  * MagViT VAE decode (AutoencoderKLMagvit.decode, autoencoder_magvit.py:271-317,381-448; Decoder,

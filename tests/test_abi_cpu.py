@@ -91,7 +91,8 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
     import subprocess
     from easyanimate_b200 import _lib as L
     pairs = {"ea_gemm_args": L.GemmArgs, "ea_qkv_args": L.QkvArgs, "ea_skinny_linear_args": L.SkinnyArgs,
-             "ea_ln_args": L.LnArgs, "ea_rmsnorm_args": L.RmsArgs, "ea_attn_args": L.AttnArgs, "ea_conv3d_args": L.ConvArgs}
+             "ea_ln_args": L.LnArgs, "ea_rmsnorm_args": L.RmsArgs, "ea_attn_args": L.AttnArgs, "ea_conv3d_args": L.ConvArgs,
+             "ea_qkv_peers": L.QkvPeers, "ea_attn_peers": L.AttnPeers}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "ea_b200.h"', 'int main(void) {']
     for cname, cls in pairs.items():
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
