@@ -133,6 +133,7 @@ ea_enable_peer_access = _sig("ea_enable_peer_access", [i32])
 ea_cfg_euler_step = _sig("ea_cfg_euler_step", [vp, vp, vp, vp, i64, f32, i32, f32, f32, vp])
 ea_l1_sums = _sig("ea_l1_sums", [vp, vp, vp, i64, vp])
 ea_ew_addsub = _sig("ea_ew_addsub", [vp, vp, vp, i64, i32, vp])
+ea_dequant_e4m3 = _sig("ea_dequant_e4m3", [vp, vp, i64, vp])
 ea_conv3d_causal = _sig("ea_conv3d_causal", [C.POINTER(ConvArgs), vp])
 ea_vae_prepare_latents = _sig("ea_vae_prepare_latents", [vp, vp, vp, vp, i64, i64, i64, i64, i64, f32, vp])
 ea_frames_out = _sig("ea_frames_out", [vp, vp, i64, i32, vp])

@@ -510,7 +510,51 @@ __global__ void ew_addsub_kernel(const bf16* __restrict__ a, const bf16* __restr
   const float2 y = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(b + i));
   *reinterpret_cast<uint32_t*>(out + i) = sub ? pack_bf16x2(x.x - y.x, x.y - y.y) : pack_bf16x2(x.x + y.x, x.y + y.y);
 }
+// e4m3fn (1-4-3, bias 7, no infinities, S.1111.111 = NaN) -> bf16, exact: every e4m3 value is a bf16 value.  The 256-entry
+// table is rebuilt per block in shared memory; 16 weights per thread (one 16-byte load, two 16-byte stores).
+__global__ void dequant_e4m3_kernel(const uint8_t* __restrict__ w8, bf16* __restrict__ w16, int64_t n) {
+  __shared__ uint16_t lut[256];
+  {
+    const int v = threadIdx.x;  // blockDim.x == 256
+    const int sgn = v >> 7, e = (v >> 3) & 15, m = v & 7;
+    float f;
+    if (e == 15 && m == 7) f = __int_as_float(0x7fc00000);
+    else if (e == 0) f = ldexpf((float)m, -9);              // subnormal: m/8 * 2^-6
+    else f = ldexpf(1.0f + (float)m * 0.125f, e - 7);
+    f = sgn ? -f : f;
+    lut[v] = __bfloat16_as_ushort(__float2bfloat16_rn(f));
+  }
+  __syncthreads();
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (i0 >= n) return;
+  if (i0 + 16 <= n) {
+    const uint4 u = *reinterpret_cast<const uint4*>(w8 + i0);
+    const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      o[2 * k] = lut[uw[k] & 0xff] | ((uint32_t)lut[(uw[k] >> 8) & 0xff] << 16);
+      o[2 * k + 1] = lut[(uw[k] >> 16) & 0xff] | ((uint32_t)lut[uw[k] >> 24] << 16);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(w16 + i0);
+    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  } else {
+    for (int64_t i = i0; i < n; ++i) w16[i] = __ushort_as_bfloat16(lut[w8[i]]);
+  }
+}
 }  // namespace ea
+
+extern "C" int ea_dequant_e4m3(const void* w8, void* w16, int64_t n, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  EA_REQUIRE(w8 && w16 && n > 0, "ea_dequant_e4m3: bad arguments");
+  EA_REQUIRE((reinterpret_cast<uintptr_t>(w8) & 15) == 0 && (reinterpret_cast<uintptr_t>(w16) & 15) == 0,
+             "ea_dequant_e4m3: pointers must be 16-byte aligned");
+  const int64_t threads = (n + 15) / 16;
+  ea::dequant_e4m3_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>((const uint8_t*)w8, (ea::bf16*)w16, n);
+  ea::count_launch();
+  return ea::check_launch("dequant_e4m3_kernel");
+}
 
 extern "C" int ea_l1_sums(const void* cur, const void* prev, void* sums, int64_t n, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

@@ -226,6 +226,16 @@ def rel_l1_from_sums(num: float, den: float, n: int) -> float:
     return float((mean_diff / mean_prev).item())
 
 
+def dequant_e4m3(w8: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """float8_e4m3fn tensor -> the same values in bf16 (exact), written into `out` (same number of elements)."""
+    if not w8.is_cuda or w8.dtype != torch.float8_e4m3fn:
+        raise L.EaError(f"dequant_e4m3 takes a CUDA float8_e4m3fn tensor, got {w8.dtype} on {w8.device}")
+    _req(out, name="out")
+    assert w8.is_contiguous() and out.is_contiguous() and out.numel() == w8.numel()
+    L.check(L.ea_dequant_e4m3(_p(w8), _p(out), w8.numel(), _stream()), "ea_dequant_e4m3")
+    return out
+
+
 def ew_add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, subtract: bool = False) -> torch.Tensor:
     _req(a, name="a"); _req(b, name="b")
     assert a.shape == b.shape and a.is_contiguous() and b.is_contiguous()

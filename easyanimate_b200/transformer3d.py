@@ -51,9 +51,12 @@ class _Attention(nn.Module):  # diffusers Attention(qk_norm="layer_norm", bias=T
         self.norm_k = nn.LayerNorm(dim_head, eps=eps)
         self.to_out = nn.ModuleList([nn.Linear(inner, dim, bias=True), nn.Dropout(0.0)])
         self._fused: Optional[tuple] = None
+        self._fused_static: Optional[tuple] = None
 
     def fused_qkv(self):
         """[3d,d] weight / [3d] bias for the fused projection kernel; rebuilt when the parameters change."""
+        if self._fused_static is not None:  # fp8 staging block: the buffers are filled by _Fp8Staging.block()
+            return self._fused_static
         ps = (self.to_q.weight, self.to_k.weight, self.to_v.weight, self.to_q.bias, self.to_k.bias, self.to_v.bias)
         key = ops.param_key(*ps)
         if self._fused is None or self._fused[0] != key:
@@ -202,6 +205,58 @@ class TeaCache:
         self.previous_residual = None
 
 
+class _Fp8Staging:
+    """bf16 staging for a model whose parameters are STORED as float8_e4m3fn - the reference's `model_cpu_offload_and_qfloat8`
+    mode (predict_t2v.py:37,106: from_pretrained_2d(torch_dtype=float8_e4m3fn); utils/fp8_optimization.py:6-35 casts every
+    module to bf16 around its own forward and back).  Same arithmetic here: every kernel consumes bf16(e4m3(w)); what stays
+    resident is the e4m3 copy (half the bytes: 11.8 GB instead of 23.6 GB for the 12B model) plus ONE block's worth of bf16
+    weights that `block()` refills with `ea_dequant_e4m3` right before the block runs, and the small non-block parameters."""
+
+    def __init__(self, model: "EasyAnimateTransformer3DModel"):
+        dev = next(model.parameters()).device
+        cfg = {k: v for k, v in model.config.items() if not k.startswith("_")}
+        cfg["num_layers"] = 0
+        with torch.device(dev):
+            self.head = EasyAnimateTransformer3DModel(**cfg).to(bf16)
+        own = dict(self.head.named_parameters())
+        for name, p8 in model.named_parameters():
+            if not name.startswith("transformer_blocks."):
+                ops.dequant_e4m3(p8.detach().contiguous(), own[name].detach())
+        self._blocks: Dict[bool, EasyAnimateDiTBlock] = {}
+        self._model_cfg = model.config
+        self._dev = dev
+
+    def _staging_block(self, mmdit: bool) -> "EasyAnimateDiTBlock":
+        if mmdit not in self._blocks:
+            c = self._model_cfg
+            d = c.num_attention_heads * c.attention_head_dim
+            with torch.device(self._dev):
+                blk = EasyAnimateDiTBlock(d, c.num_attention_heads, c.attention_head_dim, c.time_embed_dim,
+                                          c.norm_elementwise_affine, c.norm_eps, is_mmdit_block=mmdit).to(bf16)
+                for a in (blk.attn1, blk.attn2):
+                    if a is not None:
+                        a._fused_static = (torch.empty((3 * d, d), dtype=bf16), torch.empty((3 * d,), dtype=bf16))
+            self._blocks[mmdit] = blk
+        return self._blocks[mmdit]
+
+    def block(self, blk8: "EasyAnimateDiTBlock") -> "EasyAnimateDiTBlock":
+        """Expand blk8's e4m3 parameters into the staging block (stream-ordered: the previous block's kernels that read the
+        staging buffers are ahead of these writes on the same stream) and return it."""
+        st = self._staging_block(blk8.attn2 is not None)
+        dst = dict(st.named_parameters())
+        d = st.dim
+        for name, p8 in blk8.named_parameters():
+            parts = name.split(".")
+            if parts[0] in ("attn1", "attn2") and parts[1] in ("to_q", "to_k", "to_v"):
+                w, b = getattr(st, parts[0])._fused_static  # q/k/v go straight into the fused projection operand
+                i = ("to_q", "to_k", "to_v").index(parts[1])
+                out = w[i * d:(i + 1) * d] if parts[2] == "weight" else b[i * d:(i + 1) * d]
+            else:
+                out = dst[name].detach()
+            ops.dequant_e4m3(p8.detach().contiguous(), out)
+        return st
+
+
 class _Workspace:
     """Per-forward activation buffers shared by all blocks (allocated once per call through torch's caching allocator)."""
 
@@ -298,6 +353,7 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
         self.cfg_parallel_group = None  # 2-rank group holding the other CFG branch, see set_cfg_parallel_group
         self.gradient_checkpointing = False
         self._proj_w_cache: Optional[tuple] = None
+        self._fp8: Optional[tuple] = None  # (parameter key, _Fp8Staging) when the parameters are stored as float8_e4m3fn
 
     # ----------------------------------------------------------------------------------------------------------
     def enable_teacache(self, num_steps: int, rel_l1_thresh: float,
@@ -323,6 +379,12 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
 
     def _set_gradient_checkpointing(self, module, value=False):
         self.gradient_checkpointing = value
+
+    def _fp8_staging(self) -> _Fp8Staging:
+        key = ops.param_key(self.proj.weight, self.proj_out.weight)
+        if self._fp8 is None or self._fp8[0] != key:
+            self._fp8 = (key, _Fp8Staging(self))
+        return self._fp8[1]
 
     def _patch_weight(self, ldk: int) -> torch.Tensor:
         w = self.proj.weight
@@ -365,8 +427,12 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
         added_cond_kwargs: Dict[str, torch.Tensor] = None,
         return_dict=True,
     ):
-        if self.dtype != bf16:
-            raise L.EaError("easyanimate_b200 computes in bf16: call .to(torch.bfloat16) on the module first")
+        fp8 = self.dtype == torch.float8_e4m3fn
+        if self.dtype != bf16 and not fp8:
+            raise L.EaError("easyanimate_b200 computes in bf16: call .to(torch.bfloat16) on the module first (or store the "
+                            "weights as torch.float8_e4m3fn: they are expanded to bf16 block by block)")
+        staging = self._fp8_staging() if fp8 else None
+        P = staging.head if fp8 else self  # owner of the non-block parameters the kernels read
         if ref_latents is not None or clip_encoder_hidden_states is not None or timestep_cond is not None:
             raise NotImplementedError("ref_latents / clip_encoder_hidden_states / timestep_cond are outside the v5.1 "
                                       "T2V/I2V hot path")
@@ -379,7 +445,7 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
         if t.numel() == 1 and B > 1:
             t = t.expand(B).contiguous()
         temb_in = ops.timestep_embedding(t.contiguous(), d, self.config.flip_sin_to_cos, float(self.config.freq_shift))
-        te = self.time_embedding
+        te = P.time_embedding
         temb = ops.skinny_linear(temb_in, te.linear_1.weight, te.linear_1.bias)
         temb = ops.skinny_linear(temb, te.linear_2.weight, te.linear_2.bias, act_in=1)  # [B, time_embed_dim]
 
@@ -388,14 +454,14 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
         if control_latents is not None:
             extra = control_latents if extra is None else torch.cat([extra, control_latents], 1)
         a = ops.patchify(hidden_states.to(bf16), None if extra is None else extra.to(bf16))
-        x_v = ops.gemm(a, self._patch_weight(a.shape[1]), self.proj.bias)  # [B*S_v, d]
+        x_v = ops.gemm(a, P._patch_weight(a.shape[1]), P.proj.bias)  # [B*S_v, d]
         S_v = F * (H // p) * (W // p)
 
         # 3. text tokens (transformer3d.py:1533-1536)
-        x_t = self._text_tokens(self.text_proj, encoder_hidden_states.to(bf16))
+        x_t = self._text_tokens(P.text_proj, encoder_hidden_states.to(bf16))
         S_t = encoder_hidden_states.shape[1]
         if encoder_hidden_states_t5 is not None:
-            x_t5 = self._text_tokens(self.text_proj_t5, encoder_hidden_states_t5.to(bf16))
+            x_t5 = self._text_tokens(P.text_proj_t5, encoder_hidden_states_t5.to(bf16))
             S_t5 = encoder_hidden_states_t5.shape[1]
             x_t = torch.cat([x_t.view(B, S_t, d), x_t5.view(B, S_t5, d)], dim=1).reshape(B * (S_t + S_t5), d).contiguous()
             S_t += S_t5
@@ -421,7 +487,7 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
         tc = self.teacache
         should_calc = True
         if tc is not None:
-            blk0 = self.transformer_blocks[0]
+            blk0 = staging.block(self.transformer_blocks[0]) if fp8 else self.transformer_blocks[0]
             mod0 = ops.skinny_linear(temb, blk0.norm1.linear.weight, blk0.norm1.linear.bias, act_in=1)
             modulated = EasyAnimateDiTBlock._ln_mod(x_v, blk0.norm1, mod0, 0, S_v)
             if tc.cnt == 0 or tc.cnt == tc.num_steps - 1:
@@ -458,17 +524,17 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
             ori = x_v.clone() if tc is not None else None  # (device copy; the blocks update x_v in place)
             ws = _Workspace(B, S_v, S_t, d, self.num_heads, ff_inner, dev, sp=sp)
             for block in self.transformer_blocks:
-                x_v, x_t = block(x_v, x_t, temb, rope, ws)
+                x_v, x_t = (staging.block(block) if fp8 else block)(x_v, x_t, temb, rope, ws)
 
             # 5. final norms + projection (transformer3d.py:1673-1680): norm_final is row-wise, so the text rows that
             #    the reference concatenates and then drops never need to be computed.
-            mod = ops.skinny_linear(temb, self.norm_out.linear.weight, self.norm_out.linear.bias, act_in=1)  # shift|scale
-            y = ops.layernorm_modulate(x_v, self.norm_out.norm.weight, self.norm_out.norm.bias, self.norm_out.norm.eps,
+            mod = ops.skinny_linear(temb, P.norm_out.linear.weight, P.norm_out.linear.bias, act_in=1)  # shift|scale
+            y = ops.layernorm_modulate(x_v, P.norm_out.norm.weight, P.norm_out.norm.bias, P.norm_out.norm.eps,
                                        shift=mod[:, :d], scale=mod[:, d:], rows_per_batch=S_v,
-                                       pre=(self.norm_final.weight, self.norm_final.bias, self.norm_final.eps), out=ws.n_v)
+                                       pre=(P.norm_final.weight, P.norm_final.bias, P.norm_final.eps), out=ws.n_v)
             if tc is not None:
                 tc.previous_residual = ops.ew_add(y, ori, subtract=True)  # transformer3d.py:1634
-        z = ops.gemm(y, self.proj_out.weight, self.proj_out.bias)  # [B*S_v, p*p*C_out]
+        z = ops.gemm(y, P.proj_out.weight, P.proj_out.bias)  # [B*S_v, p*p*C_out]
         if sp is not None:
             z = sp.gather_tokens(z, B, S_v)  # every rank gets all S_v_full tokens back
             assert z.shape[0] == B * S_v_full

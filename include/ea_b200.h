@@ -188,6 +188,12 @@ int ea_cfg_euler_step(const void* pred_uncond, const void* pred_text, const void
 int ea_l1_sums(const void* cur, const void* prev, void* sums, int64_t n, void* stream);
 int ea_ew_addsub(const void* a, const void* b, void* out, int64_t n, int32_t subtract, void* stream);
 
+/* fp8 weight storage (the reference's "model_cpu_offload_and_qfloat8" mode: predict_t2v.py:37,106 loads the transformer with
+ * torch_dtype=float8_e4m3fn and utils/fp8_optimization.py:6-35 casts each module to bf16 around its forward): parameters stay
+ * e4m3 in HBM (half the bytes) and are expanded to bf16 - exactly, every e4m3 value is a bf16 value - into a scratch buffer
+ * right before the kernels that consume them.  n elements; both pointers 16-byte aligned. */
+int ea_dequant_e4m3(const void* w8, void* w16, int64_t n, void* stream);
+
 /* Joint text+video self-attention, non-causal, no mask, head_dim 64:  O = softmax(Q K^T * scale) V.
  * Replaces F.scaled_dot_product_attention + transpose/reshape/split at processor.py:287-303.
  * q,k,v: [B,H,S,64] bf16 contiguous.  Output is token-major and split at S_text:

@@ -234,11 +234,21 @@ def corner_blend(src, dst):
     dst[..., -Hc:, -Wc:] = (wgt * src.float() + (1 - wgt) * area).to(bf16)
 
 
+def dequant_e4m3(w8, out):
+    out.copy_(w8.to(bf16).reshape(out.shape))
+    return out
+
+
 def frames_out(video, out):
     """include/ea_b200.h ea_frames_out: the reference's op sequence on a bf16 tensor (pipeline_easyanimate.py:729,738-741)."""
     v = (video.clamp(-1, 1) / 2 + 0.5).clamp(0, 1).float()
     out.copy_(v if out.dtype == torch.float32 else (v * 255).to(torch.uint8))
     return out
+
+
+def install_fp8(monkeypatch):
+    from easyanimate_b200 import ops
+    monkeypatch.setattr(ops, "dequant_e4m3", dequant_e4m3)
 
 
 def install_vae(monkeypatch):

@@ -164,3 +164,62 @@ def test_teacache_matches_oracle_decisions_and_outputs():
             x_ref, x_our = (x_ref - 0.1 * r).to(bf16), (x_our - 0.1 * g).to(bf16)
     assert ours.teacache.skipped == ob.teacache.skipped and ours.teacache.skipped >= 1, (ours.teacache.skipped, ob.teacache.skipped)
     assert ours.teacache.cnt == 0  # reset after num_steps forwards, like the reference
+
+
+def test_fp8_weight_storage_mode_matches_reference_arithmetic():
+    """Row f4: parameters stored as float8_e4m3fn (predict_t2v.py:37,106), expanded block by block with ea_dequant_e4m3:
+    (1) the expansion is exact (every e4m3 value is a bf16 value); (2) the forward equals the bf16 forward of a model whose
+    weights are bf16(e4m3(w)) BIT FOR BIT (same kernels, same operands); (3) it is as close to the fp32 oracle with those
+    weights as the bf16 oracle is."""
+    from oracle import dit
+    from easyanimate_b200 import ops
+    from easyanimate_b200.transformer3d import EasyAnimateTransformer3DModel
+    w8 = torch.arange(256, dtype=torch.uint8, device="cuda").repeat(9).view(torch.float8_e4m3fn)
+    got = ops.dequant_e4m3(w8, torch.empty(w8.numel(), device="cuda", dtype=bf16))
+    want = w8.to(bf16)
+    assert torch.equal(torch.nan_to_num(got.float(), nan=7.0), torch.nan_to_num(want.float(), nan=7.0))
+    o32, ob, _ = _build(CFG_TINY, device="cpu")
+    q = {k: v.to(torch.float8_e4m3fn).to(bf16) for k, v in ob.state_dict().items()}
+    ob.load_state_dict(q)
+    o32.load_state_dict({k: v.float() for k, v in q.items()})
+    plain = EasyAnimateTransformer3DModel(**CFG_TINY).to(bf16)
+    plain.load_state_dict(q)
+    plain = plain.cuda()
+    stored = EasyAnimateTransformer3DModel(**CFG_TINY).to(bf16)
+    stored.load_state_dict(q)
+    stored = stored.to(torch.float8_e4m3fn).cuda()
+    assert stored.dtype == torch.float8_e4m3fn
+    B, C, F, H, W, S_t = 2, 16, 3, 8, 12, 40
+    lat, enc, t = _inputs(B, C, F, H, W, S_t, CFG_TINY["text_embed_dim"])
+    rope = dit.rope_for_video(H * 8, W * 8, F)
+    tb = t.to(bf16)
+    kw = dict(encoder_hidden_states=enc.to(bf16).cuda(), image_rotary_emb=(rope[0].cuda(), rope[1].cuda()), return_dict=False)
+    with torch.no_grad():
+        truth = o32(lat.to(bf16).float(), tb.float(), encoder_hidden_states=enc.to(bf16).float(), image_rotary_emb=rope)[0]
+        ref = ob(lat.to(bf16), tb, encoder_hidden_states=enc.to(bf16), image_rotary_emb=rope)[0]
+        a = plain(lat.to(bf16).cuda(), tb.cuda(), **kw)[0]
+        b = stored(lat.to(bf16).cuda(), tb.cuda(), **kw)[0]
+    assert torch.equal(a, b)
+    three_way(b, ref, truth, name="fp8_weight_storage")
+
+
+def test_control_latents_channel_concat():
+    """v5.1 Control: hidden | inpaint | control channel concat (transformer3d.py:1523-1526) feeding the patch-embed GEMM."""
+    from oracle import dit
+    cfg = dict(CFG_TINY, in_channels=16 + 17 + 16)
+    o32, ob, ours = _build(cfg)
+    B, F, H, W, S_t = 2, 2, 8, 8, 16
+    lat, enc, t = _inputs(B, 16, F, H, W, S_t, cfg["text_embed_dim"])
+    g = torch.Generator().manual_seed(5)
+    inp, ctl = torch.randn(B, 17, F, H, W, generator=g).to(bf16), torch.randn(B, 16, F, H, W, generator=g).to(bf16)
+    rope = dit.rope_for_video(H * 8, W * 8, F)
+    tb = t.to(bf16)
+    cat = torch.cat([inp, ctl], 1)
+    with torch.no_grad():
+        truth = o32(lat.to(bf16).float(), tb.float(), encoder_hidden_states=enc.to(bf16).float(), image_rotary_emb=rope,
+                    inpaint_latents=cat.float())[0]
+        ref = ob(lat.to(bf16), tb, encoder_hidden_states=enc.to(bf16), image_rotary_emb=rope, inpaint_latents=cat)[0]
+        got = ours(lat.to(bf16).cuda(), tb.cuda(), encoder_hidden_states=enc.to(bf16).cuda(),
+                   image_rotary_emb=(rope[0].cuda(), rope[1].cuda()), inpaint_latents=inp.cuda(), control_latents=ctl.cuda(),
+                   return_dict=False)[0]
+    three_way(got, ref, truth, name="control_latents")
