@@ -32,7 +32,7 @@ i64, i32, f32, vp = C.c_int64, C.c_int32, C.c_float, C.c_void_p
 # epilogues (keep in sync with include/ea_b200.h)
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RES, EPI_SCALE_F32, EPI_BIAS_RES = 0, 1, 2, 3, 4
 FRAMES_F32, FRAMES_U8 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class GemmArgs(C.Structure):
@@ -106,6 +106,7 @@ class ConvArgs(C.Structure):
         ("x", vp), ("w", vp), ("bias", vp), ("residual", vp), ("out", vp),
         ("T", i64), ("H", i64), ("W", i64), ("Cin", i64), ("Cout", i64), ("Cout_pad", i64),
         ("dup_frames", i32), ("out_planar", i32), ("variant", i32), ("stride_t", i32), ("stride_hw", i32),
+        ("out_row0", i32), ("out_rows", i32),
     ]
 
 
@@ -139,6 +140,8 @@ ea_vae_prepare_latents = _sig("ea_vae_prepare_latents", [vp, vp, vp, vp, i64, i6
 ea_frames_out = _sig("ea_frames_out", [vp, vp, i64, i32, vp])
 ea_groupnorm_workspace = _sig("ea_groupnorm_workspace", [i64, i64, i64], C.c_size_t)
 ea_groupnorm_stats = _sig("ea_groupnorm_stats", [vp, vp, vp, C.c_size_t, i64, i64, i64, i64, f32, vp])
+ea_groupnorm_sums = _sig("ea_groupnorm_sums", [vp, vp, vp, C.c_size_t, i64, i64, i64, i64, vp])
+ea_groupnorm_finalize = _sig("ea_groupnorm_finalize", [vp, vp, i64, i64, i64, C.c_double, f32, vp])
 ea_groupnorm_apply = _sig("ea_groupnorm_apply", [vp, vp, vp, vp, vp, i64, i64, i64, i64, i32, vp])
 ea_upsample2x = _sig("ea_upsample2x", [vp, vp, i64, i64, i64, i64, vp])
 ea_softmax_rows = _sig("ea_softmax_rows", [vp, vp, i64, i64, i64, i64, vp])

@@ -331,7 +331,14 @@ class AutoencoderKLMagvit(nn.Module, ConfigMixinLite):
         self.tile_latent_min_size = int(self.tile_sample_min_size / (2 ** (len(ch_mult) - 1)))
         self.scaling_factor = scaling_factor
         self.tile_parallel_group = None  # torch.distributed group for tile-parallel tiled_decode (one all-gather)
+        self.strip_parallel_group = None  # torch.distributed group for the strip-parallel UNTILED decode (vae_strips.py)
         self._latent_in_scale = 1.0      # decode_scaled() folds decode_latents' 1/scaling_factor into the first kernel
+
+    def set_strip_parallel_group(self, group):
+        """Shard the UNTILED decode of one video over the ranks of `group` by horizontal strips (vae_strips.py: halo rows for
+        the convolutions, all-gathered GroupNorm sums, one all-gather of the frames); every rank must call decode with the
+        same latents and gets the whole video.  None restores single-GPU decoding."""
+        self.strip_parallel_group = group
 
     def set_tile_parallel_group(self, group):
         """Shard the reference's tiled_decode tiles over the ranks of `group` (every rank must call decode with the
@@ -417,7 +424,11 @@ class AutoencoderKLMagvit(nn.Module, ConfigMixinLite):
         z = z.to(bf16)
         tl = self.tile_latent_min_size
         tiled = (self.use_tiling or self.use_tiling_decoder) and (z.shape[-1] > tl or z.shape[-2] > tl)
-        outs = [(self._tiled_decode_one(zb) if tiled else self._decode_one(zb)) for zb in z]
+        if not tiled and self.strip_parallel_group is not None:
+            from .vae_strips import decode_strips
+            outs = [decode_strips(self, zb, self.strip_parallel_group, self._latent_in_scale) for zb in z]
+        else:
+            outs = [(self._tiled_decode_one(zb) if tiled else self._decode_one(zb)) for zb in z]
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
     @torch.no_grad()

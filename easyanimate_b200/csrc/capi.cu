@@ -12,7 +12,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 }  // namespace ea
 
 extern "C" const char* ea_last_error(void) { return ea::last_error_cstr(); }
-extern "C" int ea_abi_version(void) { return 2; }
+extern "C" int ea_abi_version(void) { return 3; }
 extern "C" uint64_t ea_launch_count(void) { return ea::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int ea_enable_peer_access(int32_t peer_device) {

@@ -41,6 +41,7 @@ struct ConvDevArgs {
   int dup_frames;
   int out_planar;
   int T_out;
+  int row0, Hout;  // output row window [row0, row0 + Hout) (strip-parallel decode: the input carries halo rows), stored at row h - row0
   int st, shw;  // temporal / spatial stride (1 or 2): T, H, W above are the OUTPUT extents (see ea_conv3d_args.stride_*)
 };
 
@@ -110,7 +111,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     int r = tile / p.tiles_n;
     w0 = (r % p.tiles_w) * p.TW;
     r /= p.tiles_w;
-    h0 = ((r % p.tiles_h) * (PAIR ? 2 : 1) + crank) * (MT * p.TH);
+    h0 = p.row0 + ((r % p.tiles_h) * (PAIR ? 2 : 1) + crank) * (MT * p.TH);
     t = r / p.tiles_h;
   };
 
@@ -206,7 +207,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       for (int cc = 0; cc < MT * (BN / 32); ++cc) {
       const int m = cc / (BN / 32), c = cc % (BN / 32);
       const int h = h0 + m * p.TH + ph, w = w0 + pw;
-      const bool pix_ok = h < p.H && w < p.W;
+      const bool pix_ok = h < p.row0 + p.Hout && w < p.W;
+      const int ho = h - p.row0;
       const uint32_t trow = tmem_base + (uint32_t(ew * 32) << 16) + as * Cfg::kAccCols + m * BN;
       {
         uint32_t acc[32];
@@ -223,7 +225,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           for (int j = 0; j < 32 && col0 + j < p.Cout; ++j) {
             const float v = x[j] + __bfloat162float(p.bias[col0 + j]);
             for (int cpy = 0; cpy < ncopies; ++cpy)
-              p.out[(((int64_t)(col0 + j) * p.T_out + t_out + cpy) * p.H + h) * p.W + w] = __float2bfloat16_rn(v);
+              p.out[(((int64_t)(col0 + j) * p.T_out + t_out + cpy) * p.Hout + ho) * p.W + w] = __float2bfloat16_rn(v);
           }
           continue;
         }
@@ -240,7 +242,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         if (p.residual != nullptr) {
           // (conv2(x) + shortcut): the conv output is a bf16 tensor in the reference before the add (common.py:323)
           const uint4* rp =
-              reinterpret_cast<const uint4*>(p.residual + (((int64_t)t * p.H + h) * p.W + w) * p.Cout + col0);
+              reinterpret_cast<const uint4*>(p.residual + (((int64_t)t * p.Hout + ho) * p.W + w) * p.Cout + col0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 rr = __ldg(rp + j);
@@ -262,7 +264,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           o[j].w = pack_bf16x2(x[j * 8 + 6], x[j * 8 + 7]);
         }
         for (int cpy = 0; cpy < ncopies; ++cpy) {
-          uint4* op = reinterpret_cast<uint4*>(p.out + ((((int64_t)(t_out + cpy)) * p.H + h) * p.W + w) * p.Cout + col0);
+          uint4* op = reinterpret_cast<uint4*>(p.out + ((((int64_t)(t_out + cpy)) * p.Hout + ho) * p.W + w) * p.Cout + col0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) op[j] = o[j];
         }
@@ -295,13 +297,15 @@ static int launch_conv(const ea_conv3d_args* g, cudaStream_t stream) {
   p.H = p.shw == 2 ? (int)(g->H / 2) : (int)g->H;
   p.W = p.shw == 2 ? (int)(g->W / 2) : (int)g->W;
   p.Cin = (int)g->Cin; p.Cout = (int)g->Cout;
+  p.row0 = g->out_rows > 0 ? (int)g->out_row0 : 0;
+  p.Hout = g->out_rows > 0 ? (int)g->out_rows : p.H;
   // tile shape: 8x16 or 4x32 pixels, whichever wastes fewer out-of-range pixels
   auto waste = [&](int th, int tw) {
     th *= MT * (PAIR ? 2 : 1);
-    return (int64_t)((p.H + th - 1) / th) * th * ((p.W + tw - 1) / tw) * tw;
+    return (int64_t)((p.Hout + th - 1) / th) * th * ((p.W + tw - 1) / tw) * tw;
   };
   if (waste(4, 32) < waste(8, 16)) { p.TH = 4; p.TW = 32; } else { p.TH = 8; p.TW = 16; }
-  p.tiles_h = (p.H + (PAIR ? 2 : 1) * MT * p.TH - 1) / ((PAIR ? 2 : 1) * MT * p.TH);  // PAIR: pairs of CTA tiles
+  p.tiles_h = (p.Hout + (PAIR ? 2 : 1) * MT * p.TH - 1) / ((PAIR ? 2 : 1) * MT * p.TH);  // PAIR: pairs of CTA tiles
   p.tiles_w = (p.W + p.TW - 1) / p.TW;
   p.tiles_n = (int)((g->Cout_pad + BN - 1) / BN);
   p.kt_taps = 3;
@@ -368,6 +372,9 @@ static int launch_conv(const ea_conv3d_args* g, cudaStream_t stream) {
 
 }  // namespace ea
 
+namespace ea {
+int launch_conv3d_halo(const ea_conv3d_args* g, cudaStream_t stream);  // conv3d_halo.cu
+}
 using namespace ea;
 
 extern "C" int ea_conv3d_causal(const ea_conv3d_args* g, void* stream_) {
@@ -382,16 +389,23 @@ extern "C" int ea_conv3d_causal(const ea_conv3d_args* g, void* stream_) {
   EA_REQUIRE(g->W < 32768 && g->H < 32768, "ea_conv3d_causal: frame too large");
   EA_REQUIRE((g->stride_t == 0 || g->stride_t == 1 || g->stride_t == 2) && (g->stride_hw == 0 || g->stride_hw == 1 || g->stride_hw == 2),
              "ea_conv3d_causal: strides are 1 or 2");
+  EA_REQUIRE(g->out_rows >= 0 && g->out_row0 >= 0 && (g->out_rows == 0 || g->out_row0 + g->out_rows <= g->H),
+             "ea_conv3d_causal: output row window outside the input");
   if (g->stride_t == 2 || g->stride_hw == 2) {
+    EA_REQUIRE(g->out_rows == 0, "ea_conv3d_causal: a strided convolution takes no output row window");
     EA_REQUIRE(!g->residual && !g->dup_frames && !g->out_planar, "ea_conv3d_causal: a strided convolution takes no residual / frame "
                "duplication / planar output");
     EA_REQUIRE(g->stride_hw != 2 || (g->H >= 2 && g->W >= 2), "ea_conv3d_causal: frame too small for stride 2");
   }
+  // unit stride: one halo tile per (kt, channel slice), taps by descriptor offsets (conv3d_halo.cu; +5..18 % over the
+  // tap-per-box kernel below, profiles/r02_conv_halo_bringup.log); variant bit2 keeps the tap-per-box kernel (A/B)
+  if (g->stride_t != 2 && g->stride_hw != 2 && !(g->variant & 4)) return launch_conv3d_halo(g, stream);
   const int64_t Ho = g->stride_hw == 2 ? g->H / 2 : g->H, Wo = g->stride_hw == 2 ? g->W / 2 : g->W;
   const int64_t To = g->stride_t == 2 ? (g->T + 1) / 2 : g->T;
   // 256-pixel CTA tiles against a <=128-wide weight tile (TMEM: 2 stages x 2 sub-tiles x 128 columns) unless the
   // frame is too small to fill the SMs with them.
-  const int64_t tiles256 = To * ((Ho + 15) / 16) * ((Wo + 15) / 16) * ((g->Cout_pad + 127) / 128);
+  const int64_t Hw = g->out_rows > 0 ? g->out_rows : Ho;  // rows actually computed
+  const int64_t tiles256 = To * ((Hw + 15) / 16) * ((Wo + 15) / 16) * ((g->Cout_pad + 127) / 128);
   const bool big = tiles256 >= 2 * sm_count() && !(g->variant & 1);
   // CTA pairs (variant bit1 disables them: A/B measurements) once there are at least four waves of pair tiles
   const bool pairs = big && !(g->variant & 2) && tiles256 >= 8 * sm_count();

@@ -105,6 +105,36 @@ __global__ void gn_finalize_kernel(const double* __restrict__ part, float* __res
   stats[2 * i] = (float)mean;
   stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
+// Strip-parallel decode: the block partials of ONE rank's rows reduced to a (sum, sum of squares) pair per (frame, group) ...
+__global__ void gn_sums_kernel(const double* __restrict__ part, double* __restrict__ sums, int n, int G, int blocks) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (frame, group)
+  if (i >= n) return;
+  const int t = i / G, g = i % G;
+  double a = 0.0, b = 0.0;
+  for (int bx = 0; bx < blocks; ++bx) {
+    const double* src = part + (((int64_t)t * blocks + bx) * G + g) * 2;
+    a += src[0];
+    b += src[1];
+  }
+  sums[2 * i] = a;
+  sums[2 * i + 1] = b;
+}
+// ... and the statistics from the gathered pairs of all `parts` ranks, added in rank order (identical on every rank)
+__global__ void gn_finalize_parts_kernel(const double* __restrict__ sums, float* __restrict__ stats, int n, int parts,
+                                         double count, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a = 0.0, b = 0.0;
+  for (int r = 0; r < parts; ++r) {
+    a += sums[((int64_t)r * n + i) * 2];
+    b += sums[((int64_t)r * n + i) * 2 + 1];
+  }
+  const double mean = a / count;
+  double var = b / count - mean * mean;
+  var = var < 0 ? 0 : var;
+  stats[2 * i] = (float)mean;
+  stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
 // y = [silu](bf16((x - mean) * rstd * gamma + beta)); one 8-channel vector per thread
 __global__ void gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const bf16* __restrict__ gamma,
                                 const bf16* __restrict__ beta, const float* __restrict__ stats, int64_t HW, int C, int G,
@@ -361,6 +391,37 @@ extern "C" int ea_groupnorm_stats(const void* x, void* stats, void* workspace, s
                                                           blocks_x, (double)HW * (double)(C / groups), eps);
   count_launch();
   return check_launch("groupnorm_stats");
+}
+
+extern "C" int ea_groupnorm_sums(const void* x, void* sums, void* workspace, size_t workspace_bytes, int64_t frames,
+                                 int64_t HW, int64_t C, int64_t groups, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  EA_REQUIRE(x && sums && workspace, "ea_groupnorm_sums: null pointer");
+  EA_REQUIRE(C % 8 == 0 && C % groups == 0 && C <= 2048 && 256 % (C / 8) == 0,
+             "ea_groupnorm_sums: C must be a multiple of 8 dividing into 256 threads, and of groups");
+  if (workspace_bytes < ea_groupnorm_workspace(frames, HW, groups))
+    return fail(EA_ERR_WORKSPACE, "ea_groupnorm_sums: workspace too small");
+  EA_REQUIRE(frames <= 65535, "ea_groupnorm_sums: too many frames");
+  const int blocks_x = gn_blocks(HW);
+  const int pix_per_block = (int)((HW + blocks_x - 1) / blocks_x);
+  dim3 grid((unsigned)blocks_x, (unsigned)frames);
+  const size_t smem = 2 * (size_t)(256 / (C / 8)) * C * sizeof(float);
+  gn_partial_kernel<<<grid, 256, smem, stream>>>((const bf16*)x, (double*)workspace, HW, (int)C, (int)groups, pix_per_block);
+  count_launch();
+  const int n = (int)(frames * groups);
+  gn_sums_kernel<<<(n + 127) / 128, 128, 0, stream>>>((const double*)workspace, (double*)sums, n, (int)groups, blocks_x);
+  count_launch();
+  return check_launch("groupnorm_sums");
+}
+
+extern "C" int ea_groupnorm_finalize(const void* sums, void* stats, int64_t parts, int64_t frames, int64_t groups, double count,
+                                     float eps, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  EA_REQUIRE(sums && stats && parts > 0 && frames > 0 && groups > 0 && count > 0, "ea_groupnorm_finalize: bad arguments");
+  const int n = (int)(frames * groups);
+  gn_finalize_parts_kernel<<<(n + 127) / 128, 128, 0, stream>>>((const double*)sums, (float*)stats, n, (int)parts, count, eps);
+  count_launch();
+  return check_launch("gn_finalize_parts_kernel");
 }
 
 extern "C" int ea_groupnorm_apply(const void* x, void* y, const void* gamma, const void* beta, const void* stats,

@@ -14,10 +14,11 @@ from . import _lib as L
 
 bf16 = torch.bfloat16
 ATTN_TIMING = None  # set to a list by bench.py to collect (start, end) CUDA events around every attention launch
-# attention kernel selector (include/ea_b200.h `ea_attn_args.variant`): 0x10c = sixth-generation kernel (one TMEM pass,
-# no per-block row maximum on the hot path, all exponentials on MUFU) — the fastest measured on B200
-# (profiles/r01_attn_microbench_*.log).  The retired generations exist only in A/B builds (EA_ATTN_AB=1 build.sh).
-ATTN_VARIANT = int(os.environ.get("EA_ATTN_VARIANT", "0x10c"), 0)
+# attention kernel selector (include/ea_b200.h `ea_attn_args.variant`): 0x210c = sixth-generation kernel (one TMEM pass,
+# no per-block row maximum on the hot path, all exponentials on MUFU) in its 3 query tiles x 64-key-block layout: 932
+# TFLOP/s at 47 056 tokens against 890 for the 2 x 128 layout (0x10c) on the same box (profiles/r02_attn_microbench_3x64.log).
+# The retired generations exist only in A/B builds (EA_ATTN_AB=1 build.sh).
+ATTN_VARIANT = int(os.environ.get("EA_ATTN_VARIANT", "0x210c"), 0)
 ATTN_GENERATIONS = L.ea_attn_generations()  # bit 6 always; bits 1, 4, 9 in A/B builds
 
 

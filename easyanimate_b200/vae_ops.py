@@ -11,27 +11,33 @@ import torch
 from . import _lib as L
 from .ops import _p, _req, _stream, bf16, gemm
 
-CONV_VARIANT = int(os.environ.get("EA_CONV_VARIANT", "0"), 0)  # bit0: force 128-pixel CTA tiles, bit1: no CTA pairs (A/B)
+CONV_VARIANT = int(os.environ.get("EA_CONV_VARIANT", "0"), 0)  # A/B bits, include/ea_b200.h ea_conv3d_args.variant (bit2: tap-per-box kernel)
 
 
 def conv3d_causal(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, cout: int, *,
                   residual: Optional[torch.Tensor] = None, dup_frames: bool = False, out_planar: bool = False,
-                  stride_t: int = 1, stride_hw: int = 1) -> torch.Tensor:
+                  stride_t: int = 1, stride_hw: int = 1, out_row0: int = 0, out_rows: int = 0) -> torch.Tensor:
     """x [T,H,W,Cin] -> [T',H',W',cout] (or planar [cout,T',H,W]); w_packed [Cout_pad, 27*Cin] from pack_conv_weight.
-    stride_hw / stride_t = 2: the encoder's down-sampling convolutions (include/ea_b200.h ea_conv3d_args.stride_*)."""
+    stride_hw / stride_t = 2: the encoder's down-sampling convolutions (include/ea_b200.h ea_conv3d_args.stride_*).
+    out_rows > 0: only output rows [out_row0, out_row0 + out_rows) are computed (x carries halo rows around the window;
+    strip-parallel decode) and the result / residual have out_rows rows."""
     _req(x, name="x"); _req(w_packed, name="w")
     T, H, W, Cin = x.shape
     assert x.is_contiguous() and w_packed.is_contiguous() and w_packed.shape[1] == 27 * Cin, (x.shape, w_packed.shape)
     T_out = 2 * T - 1 if dup_frames else ((T + 1) // 2 if stride_t == 2 else T)
     if stride_hw == 2:
         H, W = H // 2, W // 2
+    if out_rows > 0:
+        assert stride_hw == 1 and stride_t == 1 and 0 <= out_row0 and out_row0 + out_rows <= H
+        H = out_rows
     shape = (cout, T_out, H, W) if out_planar else (T_out, H, W, cout)
     out = torch.empty(shape, device=x.device, dtype=bf16)
     if residual is not None:
         assert residual.shape == (T, H, W, cout) and residual.is_contiguous()
     args = L.ConvArgs(x=_p(x), w=_p(w_packed), bias=_p(bias), residual=_p(residual), out=_p(out), T=T, H=x.shape[1], W=x.shape[2],
                       Cin=Cin, Cout=cout, Cout_pad=w_packed.shape[0], dup_frames=int(dup_frames),
-                      out_planar=int(out_planar), variant=CONV_VARIANT, stride_t=stride_t, stride_hw=stride_hw)
+                      out_planar=int(out_planar), variant=CONV_VARIANT, stride_t=stride_t, stride_hw=stride_hw,
+                      out_row0=out_row0, out_rows=out_rows)
     L.check(L.ea_conv3d_causal(C.byref(args), _stream()), "ea_conv3d_causal")
     return out
 
@@ -88,6 +94,34 @@ def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: 
     return y
 
 
+def groupnorm_sums(x: torch.Tensor, groups: int) -> torch.Tensor:
+    """(sum, sum of squares) per (frame, group) of THIS rank's rows x [T,Hs,W,C] -> float64 [T, groups, 2] (strip-parallel decode)."""
+    _req(x, name="x")
+    T, H, W, Cc = x.shape
+    assert x.is_contiguous()
+    sums = torch.empty((T, groups, 2), device=x.device, dtype=torch.float64)
+    ws_bytes = L.ea_groupnorm_workspace(T, H * W, groups)
+    ws = torch.empty((ws_bytes,), device=x.device, dtype=torch.uint8)
+    L.check(L.ea_groupnorm_sums(_p(x), _p(sums), _p(ws), ws_bytes, T, H * W, Cc, groups, _stream()), "ea_groupnorm_sums")
+    return sums
+
+
+def groupnorm_from_sums(x: torch.Tensor, sums_all: torch.Tensor, count: float, gamma: torch.Tensor, beta: torch.Tensor,
+                        groups: int, eps: float, silu: bool) -> torch.Tensor:
+    """Per-frame GroupNorm (+SiLU) of this rank's rows with statistics from the gathered sums of ALL ranks
+    (sums_all float64 [parts, T, groups, 2], added in rank order; count = pixels of the whole frame x channels per group)."""
+    _req(x, name="x")
+    T, H, W, Cc = x.shape
+    assert sums_all.dtype == torch.float64 and sums_all.is_contiguous() and sums_all.shape[1:] == (T, groups, 2)
+    stats = torch.empty((T, groups, 2), device=x.device, dtype=torch.float32)
+    L.check(L.ea_groupnorm_finalize(_p(sums_all), _p(stats), sums_all.shape[0], T, groups, float(count), eps, _stream()),
+            "ea_groupnorm_finalize")
+    y = torch.empty_like(x)
+    L.check(L.ea_groupnorm_apply(_p(x), _p(y), _p(gamma), _p(beta), _p(stats), T, H * W, Cc, groups, int(silu), _stream()),
+            "ea_groupnorm_apply")
+    return y
+
+
 def upsample2x(x: torch.Tensor) -> torch.Tensor:
     _req(x, name="x")
     T, H, W, Cc = x.shape
@@ -114,21 +148,26 @@ def transpose2d(x: torch.Tensor, ldo: int) -> torch.Tensor:
 
 
 def spatial_attention(n: torch.Tensor, w_qkv: torch.Tensor, b_qkv: torch.Tensor, w_out: torch.Tensor, b_out: torch.Tensor,
-                      residual: torch.Tensor, frames: int, scale: float) -> torch.Tensor:
-    """AttnProcessor2_0 (attention_processors.py:105-137) per frame with one head: n, residual [frames*HW, C]."""
+                      residual: torch.Tensor, frames: int, scale: float, q_rows: Optional[tuple] = None) -> torch.Tensor:
+    """AttnProcessor2_0 (attention_processors.py:105-137) per frame with one head: n [frames*HW, C].
+    q_rows = (p0, p1): strip-parallel decode - n holds ALL pixels of every frame (gathered), only the queries of pixels
+    [p0, p1) of each frame are evaluated (against all keys) and residual / the result are [frames*(p1-p0), C]."""
     M, Cc = n.shape
     HW = M // frames
+    p0, p1 = q_rows if q_rows is not None else (0, HW)
+    nq = p1 - p0
     qkv = gemm(n, w_qkv, b_qkv)  # [M, 3C]
     ld = (HW + 7) // 8 * 8
-    o = torch.empty((M, Cc), device=n.device, dtype=bf16)
+    o = torch.empty((frames * nq, Cc), device=n.device, dtype=bf16)
     for f in range(frames):
         rows = slice(f * HW, (f + 1) * HW)
-        q, k, v = qkv[rows, 0:Cc], qkv[rows, Cc:2 * Cc], qkv[rows, 2 * Cc:3 * Cc]
-        s = torch.empty((HW, ld), device=n.device, dtype=torch.float32)[:, :HW]
-        gemm(q, k, None, epilogue=L.EPI_SCALE_F32, scale=scale, out=s)  # [HW, HW] fp32 scores
+        qr = slice(f * HW + p0, f * HW + p1)
+        q, k, v = qkv[qr, 0:Cc], qkv[rows, Cc:2 * Cc], qkv[rows, 2 * Cc:3 * Cc]
+        s = torch.empty((nq, ld), device=n.device, dtype=torch.float32)[:, :HW]
+        gemm(q, k, None, epilogue=L.EPI_SCALE_F32, scale=scale, out=s)  # [nq, HW] fp32 scores
         p = softmax_rows(s, ld)
         vt = transpose2d(v, ld)  # [C, ld]
-        gemm(p[:, :HW], vt[:, :HW], None, out=o[rows])
+        gemm(p[:, :HW], vt[:, :HW], None, out=o[f * nq:(f + 1) * nq])
     return gemm(o, w_out, b_out, epilogue=L.EPI_BIAS_RES, residual=residual)
 
 

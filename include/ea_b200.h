@@ -199,10 +199,12 @@ int ea_dequant_e4m3(const void* w8, void* w16, int64_t n, void* stream);
  * q,k,v: [B,H,S,64] bf16 contiguous.  Output is token-major and split at S_text:
  * out_text[B,S_text,H*64], out_video[B,S-S_text,H*64].
  * variant selects the kernel (all produce the same softmax):
- *   0x10c (the Python layer's default): sixth generation - two query tiles per CTA, one TMEM pass, exponentials against
+ *   0x10c: sixth generation - two query tiles per CTA, 128-key blocks, one TMEM pass, exponentials against
  *     the reference kept from earlier key blocks with an end-of-block overflow verdict instead of a per-block row
  *     maximum; bits 4-6: 0-3 = that many of every 4 column pairs by a polynomial on the FMA pipe instead of MUFU,
- *     5/6 = 1/2 of 4 in two phases; bit11 (0x800): P packed by truncation instead of round-to-nearest.
+ *     5/6 = 1/2 of 4 in two phases; bit11 (0x800): P packed by truncation instead of round-to-nearest;
+ *     bit13 (0x2000): three query tiles per CTA and 64-key blocks (three softmax warps per SM sub-partition) -
+ *     0x210c is the Python layer's default.
  *   Other values select retired generations (first: bits 0-1, fourth: 0x0c|poly<<4, ninth: 0x1000|...), present only in an
  *   A/B build (EA_ATTN_AB=1 build.sh; tools/attn_ab/); ea_attn_generations() returns the bitmask of generations built
  *   in (bit 6 always).  Anything else is EA_ERR_INVALID. */
@@ -256,12 +258,20 @@ typedef struct {
   int64_t T, H, W, Cin, Cout, Cout_pad;
   int32_t dup_frames;
   int32_t out_planar;
-  int32_t variant;      /* 0 = default tiling; bit0: force 128-pixel CTA tiles, bit1: no CTA pairs (A/B measurements) */
+  int32_t variant;      /* 0 = default tiling; bit0: force 128-pixel CTA tiles, bit1: no CTA pairs (A/B measurements);
+                         * bit2: tap-per-box kernel for unit-stride calls too (default: halo-tile kernel - one shared-memory
+                         * halo tile per (kt, channel slice), the nine spatial taps by descriptor offsets); bit4: the other
+                         * halo pitch (A/B) */
   /* Encoder down-sampling convolutions (downsamplers.py:24-96: F.pad(x, (0,1,0,1)) then CausalConv3d(stride=(s_t,2,2),
    * padding 0)): stride_hw = 2 -> out[t,i,j] reads input rows 2i..2i+2 / columns 2j..2j+2 (zeros past the bottom / right
    * edge), out is [T', H/2, W/2, Cout]; stride_t = 2 -> out frame t reads input frames 2t-2..2t (clamped at 0), T' = (T+1)/2.
    * 0 or 1 = unit stride.  Strided calls take no residual / dup_frames / out_planar. */
   int32_t stride_t, stride_hw;
+  /* Output row window (strip-parallel decode, SURVEY.md section 8(e) "by spatial strips"): out_rows > 0 -> only output rows
+   * [out_row0, out_row0 + out_rows) of the H input rows are computed and `out` / `residual` are [T', out_rows, W, Cout]
+   * (planar: [Cout, T', out_rows, W]); the input then carries its neighbours' halo rows (or zeros at the frame edge) above
+   * and below the window.  0 = all rows.  Unit stride only. */
+  int32_t out_row0, out_rows;
 } ea_conv3d_args;
 
 int ea_conv3d_causal(const ea_conv3d_args* args, void* stream);
@@ -285,6 +295,15 @@ size_t ea_groupnorm_workspace(int64_t frames, int64_t HW, int64_t groups);
 int ea_groupnorm_stats(const void* x, void* stats, void* workspace, size_t workspace_bytes, int64_t frames, int64_t HW,
                        int64_t C, int64_t groups, float eps, void* stream);
 /* y = [SiLU](bf16((x-mean)*rstd*gamma+beta)) */
+/* Strip-parallel decode (one frame sequence split into row strips over several GPUs): the per-frame
+ * GroupNorm statistics are global, so each GPU reduces ITS rows to (sum, sum of squares) per (frame, group) in fp64
+ * [frames, groups, 2] (ea_groupnorm_sums; workspace as ea_groupnorm_stats), the pairs of all GPUs are gathered
+ * [parts, frames, groups, 2] and added in rank order into the same mean / rstd on every GPU (ea_groupnorm_finalize; count =
+ * pixels of the WHOLE frame x channels per group).  With parts = 1 the result equals ea_groupnorm_stats. */
+int ea_groupnorm_sums(const void* x, void* sums, void* workspace, size_t workspace_bytes, int64_t frames, int64_t HW, int64_t C,
+                      int64_t groups, void* stream);
+int ea_groupnorm_finalize(const void* sums, void* stats, int64_t parts, int64_t frames, int64_t groups, double count, float eps,
+                          void* stream);
 int ea_groupnorm_apply(const void* x, void* y, const void* gamma, const void* beta, const void* stats, int64_t frames,
                        int64_t HW, int64_t C, int64_t groups, int32_t silu, void* stream);
 

@@ -156,7 +156,8 @@ def install(monkeypatch):
 # -----------------------------------------------------------------------------------------------------------------------
 # VAE entry points (easyanimate_b200.vae_ops): channels-last [T,H,W,C] activations for one batch element
 # -----------------------------------------------------------------------------------------------------------------------
-def conv3d_causal(x, w_packed, bias, cout, *, residual=None, dup_frames=False, out_planar=False, stride_t=1, stride_hw=1):
+def conv3d_causal(x, w_packed, bias, cout, *, residual=None, dup_frames=False, out_planar=False, stride_t=1, stride_hw=1,
+                  out_row0=0, out_rows=0):
     T, H, W, Cin = x.shape
     w = w_packed.float().view(w_packed.shape[0], 3, 3, 3, Cin).permute(0, 4, 1, 2, 3)[:cout]  # [cout,Cin,kt,kh,kw]
     xin = x.float().permute(3, 0, 1, 2)[None]  # [1,Cin,T,H,W]
@@ -166,6 +167,8 @@ def conv3d_causal(x, w_packed, bias, cout, *, residual=None, dup_frames=False, o
         y = torch.nn.functional.conv3d(xin, w, bias.float()[:cout], stride=(stride_t, 2, 2))[0]
     else:
         y = torch.nn.functional.conv3d(xin, w, bias.float()[:cout], padding=(0, 1, 1), stride=(stride_t, 1, 1))[0]  # [cout,T,H,W]
+    if out_rows > 0:  # ea_conv3d_args.out_row0 / out_rows: only the window's rows exist in the output
+        y = y[:, :, out_row0:out_row0 + out_rows]
     y = _r(y)
     if residual is not None:
         y = _r(y + residual.float().permute(3, 0, 1, 2))
@@ -194,17 +197,42 @@ def groupnorm(x, gamma, beta, groups, eps, silu):
     return y.permute(0, 2, 3, 1).contiguous().to(bf16)
 
 
+def groupnorm_sums(x, groups):
+    T, H, W, C = x.shape
+    xg = x.double().view(T, H * W, groups, C // groups)
+    return torch.stack([xg.sum(dim=(1, 3)), (xg * xg).sum(dim=(1, 3))], dim=-1).contiguous()  # [T, G, 2] fp64
+
+
+def groupnorm_from_sums(x, sums_all, count, gamma, beta, groups, eps, silu):
+    T, H, W, C = x.shape
+    tot = torch.zeros_like(sums_all[0])
+    for r in range(sums_all.shape[0]):  # rank order, like ea_groupnorm_finalize
+        tot = tot + sums_all[r]
+    mean = tot[..., 0] / count
+    var = (tot[..., 1] / count - mean * mean).clamp_min(0)
+    mean, rstd = mean.float(), (1.0 / torch.sqrt(var + eps)).float()  # [T, G]
+    cpg = C // groups
+    m = mean.repeat_interleave(cpg, dim=1)[:, None, None, :]
+    r_ = rstd.repeat_interleave(cpg, dim=1)[:, None, None, :]
+    y = _r((x.float() - m) * r_ * gamma.float() + beta.float())
+    if silu:
+        y = _r(torch.nn.functional.silu(y))
+    return y.contiguous().to(bf16)
+
+
 def upsample2x(x):
     return x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2).contiguous()
 
 
-def spatial_attention(n, w_qkv, b_qkv, w_out, b_out, residual, frames, scale):
+def spatial_attention(n, w_qkv, b_qkv, w_out, b_out, residual, frames, scale, q_rows=None):
     M, C = n.shape
     HW = M // frames
     qkv = _r(n.float() @ w_qkv.float().t() + b_qkv.float()).view(frames, HW, 3, C)
     q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    if q_rows is not None:
+        q = q[:, q_rows[0]:q_rows[1]]
     p = _r(torch.softmax(q @ k.transpose(1, 2) * scale, dim=-1))
-    o = _r(p @ v).reshape(M, C)
+    o = _r(p @ v).reshape(-1, C)
     return _r(_r(o @ w_out.float().t() + b_out.float()) + residual.float()).to(bf16)
 
 
@@ -253,8 +281,8 @@ def install_fp8(monkeypatch):
 
 def install_vae(monkeypatch):
     from easyanimate_b200 import ops, vae_ops
-    for name in ("conv3d_causal", "prepare_latents", "groupnorm", "upsample2x", "spatial_attention", "tile_blend", "copy2d",
-                 "corner_blend", "frames_out"):
+    for name in ("conv3d_causal", "prepare_latents", "groupnorm", "groupnorm_sums", "groupnorm_from_sums", "upsample2x",
+                 "spatial_attention", "tile_blend", "copy2d", "corner_blend", "frames_out"):
         monkeypatch.setattr(vae_ops, name, globals()[name])
     monkeypatch.setattr(ops, "gemm", gemm)
 

@@ -112,3 +112,86 @@ def test_vae_tile_parallel_decode_equals_single_process_tiled_decode():
         importlib.reload(vae_ops)
     assert single.shape == (1, 3, 5, 112, 104)
     assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][1], single)
+
+
+# ---- strip-parallel UNTILED decode (easyanimate_b200/vae_strips.py): halo rows, gathered GroupNorm sums, gathered frames ----
+def _strip_decode(group, h=11, w=6):
+    from oracle import vae
+    from easyanimate_b200.autoencoder_magvit import AutoencoderKLMagvit
+    boc = [64, 64, 128, 128]
+    ob = vae.init_weights_(vae.OracleAutoencoderKLMagvit(block_out_channels=boc), 33)
+    m = AutoencoderKLMagvit(latent_channels=16, cache_mag_vae=True, spatial_group_norm=True, mid_block_attention_type="spatial",
+                            block_out_channels=boc).to(bf16)
+    m.load_state_dict({k: v.to(bf16) for k, v in ob.state_dict().items()}, strict=False)
+    z = torch.randn(16, 2, h, w, generator=torch.Generator().manual_seed(8)).to(bf16)
+    with torch.no_grad():  # (decode() itself refuses CPU tensors: the two branches of _decode are called directly)
+        if group is None:
+            return m._decode_one(z)
+        from easyanimate_b200.vae_strips import decode_strips
+        return decode_strips(m, z, group)
+
+
+def _install_cpu_strip_ops():
+    from easyanimate_b200 import vae_ops
+    from tests import cpu_ops
+    _install_cpu_vae_ops()
+    for name in ("groupnorm_sums", "groupnorm_from_sums"):
+        setattr(vae_ops, name, getattr(cpu_ops, name))
+
+    def groupnorm_one_part(x, gamma, beta, groups, eps, silu):
+        # the single-process decode through the SAME stand-in arithmetic as the strips (on the GPU both forms end in the same
+        # apply kernel; F.group_norm rounds differently from the explicit (x - mean) * rstd form)
+        T, H, W, C = x.shape
+        return cpu_ops.groupnorm_from_sums(x, cpu_ops.groupnorm_sums(x, groups)[None], float(H * W * (C // groups)), gamma, beta,
+                                           groups, eps, silu)
+    vae_ops.groupnorm = groupnorm_one_part
+
+
+def _strip_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    _install_cpu_strip_ops()
+    out = _strip_decode(dist.new_group(list(range(world))))
+    q.put((rank, out.float()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run_strips(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 90) + world
+    procs = [ctx.Process(target=_strip_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return [r[1] for r in res]
+
+
+def test_vae_strip_parallel_decode_equals_single_process_untiled_decode():
+    """11 latent rows over 2 and over 3 ranks (uneven strips, a middle rank with two neighbours): every rank ends with the whole
+    video, identical across ranks, and equal to the single-process untiled decode up to bf16 round-off.  With the torch
+    stand-ins every layer at latent resolution (conv_in, mid block with attention, first up block) is bit-identical; from the
+    first up-sampled convolution on, PyTorch's CPU conv3d blocks a strip-shaped input differently from the full frame (fp32
+    summation order), which flips a few bf16 roundings that a random-init network then spreads - hence a tolerance here.  On
+    the GPU the convolution's k order does not depend on the strip (tools/test_multigpu.py checks that decode)."""
+    import importlib
+    from easyanimate_b200 import ops, vae_ops
+    _install_cpu_strip_ops()
+    try:
+        single = _strip_decode(None).float()
+    finally:
+        importlib.reload(ops)
+        importlib.reload(vae_ops)
+    assert single.shape == (1, 3, 5, 88, 48)
+    for world in (2, 3):
+        outs = _run_strips(world)
+        for o in outs[1:]:
+            assert torch.equal(o, outs[0])
+        diff = (outs[0] - single).abs()
+        scale = single.abs().max().item()
+        assert diff.max().item() <= 0.05 * scale, (world, diff.max().item(), scale)
+        assert diff.mean().item() <= 0.004 * scale, (world, diff.mean().item(), scale)

@@ -54,6 +54,62 @@ def test_conv3d_causal(T, H, W, Cin, Cout):
         assert out3.shape[0] == 2 * T - 1 and torch.equal(out3, out[idx])
 
 
+@pytest.mark.parametrize("T,H,W,Cin,Cout", [(2, 21, 24, 64, 128), (3, 70, 160, 128, 256), (3, 300, 250, 64, 128)])
+@pytest.mark.parametrize("variant", [0, 4])
+def test_conv3d_output_row_window_is_the_same_convolution(T, H, W, Cin, Cout, variant, monkeypatch):
+    """ea_conv3d_args.out_row0 / out_rows (strip-parallel decode): the rows of a window are bit-identical to the same rows of the
+    whole-frame convolution, with residual, frame duplication and the planar store - both kernel families."""
+    from easyanimate_b200 import vae_ops
+    monkeypatch.setattr(vae_ops, "CONV_VARIANT", variant)
+    x = _rand((T, H, W, Cin), 1.0, 1)
+    w = vae_ops.pack_conv_weight(_rand((Cout, Cin, 3, 3, 3), (27 * Cin) ** -0.5, 2))
+    b = _rand((Cout,), 0.1, 3)
+    res = _rand((T, H, W, Cout), 1.0, 4)
+    full = vae_ops.conv3d_causal(x, w, b, Cout, residual=res, dup_frames=T > 1)
+    for (r0, r1) in ((0, 7), (5, H - 3), (H - 9, H)):
+        lo, hi = max(r0 - 1, 0), min(r1 + 1, H)  # the window plus one halo row where the frame continues
+        win = vae_ops.conv3d_causal(x[:, lo:hi].contiguous(), w, b, Cout, residual=res[:, r0:r1].contiguous(), dup_frames=T > 1,
+                                    out_row0=r0 - lo, out_rows=r1 - r0)
+        if lo == r0 or hi == r1:  # the frame edge: zero padding is what both see
+            pass
+        assert torch.equal(win, full[:, r0:r1]), (r0, r1)
+    w3 = vae_ops.pack_conv_weight(_rand((3, Cin, 3, 3, 3), (27 * Cin) ** -0.5, 5), cout_pad=32)
+    b3 = _rand((3,), 0.1, 6)
+    fullp = vae_ops.conv3d_causal(x, w3, b3, 3, out_planar=True)
+    winp = vae_ops.conv3d_causal(x[:, 4:15].contiguous(), w3, b3, 3, out_planar=True, out_row0=1, out_rows=9)
+    assert torch.equal(winp, fullp[:, :, 5:14])
+
+
+def test_groupnorm_from_gathered_sums_and_attention_query_rows():
+    """The strip-parallel forms of GroupNorm and of the mid-block attention: one part == ea_groupnorm_stats bit for bit, two
+    parts (rows split 9 + 12) the same up to the association of two fp64 additions; query rows [p0, p1) of the attention are
+    the same rows of the full evaluation."""
+    from easyanimate_b200 import vae_ops
+    T, H, W, Cc, G = 3, 21, 16, 128, 32
+    x = _rand((T, H, W, Cc), 2.0, 1) + 0.5
+    gamma, beta = _rand((Cc,), 0.1, 2) + 1.0, _rand((Cc,), 0.1, 3)
+    ref = vae_ops.groupnorm(x, gamma, beta, G, 1e-6, True)
+    count = float(H * W * (Cc // G))
+    one = vae_ops.groupnorm_from_sums(x, vae_ops.groupnorm_sums(x, G)[None].contiguous(), count, gamma, beta, G, 1e-6, True)
+    assert torch.equal(one, ref)
+    a, b = x[:, :9].contiguous(), x[:, 9:].contiguous()
+    sums = torch.stack([vae_ops.groupnorm_sums(a, G), vae_ops.groupnorm_sums(b, G)]).contiguous()
+    two = torch.cat([vae_ops.groupnorm_from_sums(a, sums, count, gamma, beta, G, 1e-6, True),
+                     vae_ops.groupnorm_from_sums(b, sums, count, gamma, beta, G, 1e-6, True)], dim=1)
+    assert (two.float() - ref.float()).abs().max().item() <= 2 ** -7 * ref.float().abs().max().item()
+    assert (two != ref).float().mean().item() < 1e-3
+    # attention query rows
+    C2 = 128
+    n, res = _rand((T * H * W, C2), 1.0, 4), _rand((T * H * W, C2), 1.0, 5)
+    wq, bq = _rand((3 * C2, C2), C2 ** -0.5, 6), _rand((3 * C2,), 0.1, 7)
+    wo, bo = _rand((C2, C2), C2 ** -0.5, 8), _rand((C2,), 0.1, 9)
+    full = vae_ops.spatial_attention(n, wq, bq, wo, bo, res, T, C2 ** -0.5).view(T, H * W, C2)
+    p0, p1 = 5 * W, 17 * W
+    part = vae_ops.spatial_attention(n, wq, bq, wo, bo, res.view(T, H * W, C2)[:, p0:p1].reshape(-1, C2).contiguous(), T, C2 ** -0.5,
+                                     q_rows=(p0, p1)).view(T, p1 - p0, C2)
+    assert torch.equal(part, full[:, p0:p1])
+
+
 def test_conv3d_planar_rgb_and_padded_input_channels():
     from easyanimate_b200 import vae_ops
     T, H, W = 3, 16, 24
