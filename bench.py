@@ -659,6 +659,7 @@ def main():
     # secondary lines (other BASELINE configs), all ranks take part when N > 1
     # =============================================================================================================
     secondary = {}
+    model.set_sequence_parallel_group(None)  # (collective) unmaps the peers' exchange buffers before they are freed
     del model, sampler
     torch.cuda.empty_cache()
     want_secondary = not args.no_secondary and not tiny
@@ -671,6 +672,7 @@ def main():
         secondary["R720_12B"] = {"value": 3e3 / ms12 * (n_videos if not single_video else 1), "unit": "steps/s", "ms_per_step": ms12 / 3,
                                  "steps": 3, "warmup": 2, "params": sum(p.numel() for p in m12.parameters()),
                                  "model_tflops": fl12 * 3 / ms12 / 1e9 * (n_videos if not single_video else 1), "tflop_per_step": fl12 / 1e12}
+        m12.set_sequence_parallel_group(None)
         del m12, s12
         torch.cuda.empty_cache()
     if want_secondary and world == 1:
@@ -683,6 +685,7 @@ def main():
         secondary["R1024_12B_I2V"] = {"value": 2e3 / msi, "unit": "steps/s", "ms_per_step": msi / 2, "steps": 2, "warmup": 2,
                                       "tokens": pi["F"] * (pi["h"] // 2) * (pi["w"] // 2) + S_TEXT, "model_tflops": fli * 2 / msi / 1e9,
                                       "tflop_per_step": fli / 1e12}
+        mi.set_sequence_parallel_group(None)
         del mi, si
         torch.cuda.empty_cache()
 
@@ -717,7 +720,31 @@ def main():
         if rank == 0:
             line["vae_decode"] = {"value": y.shape[2] * y.shape[3] * y.shape[4] / 1e6 / ms_v * 1e3, "unit": "MPix/s", "ms": ms_v,
                                   "mode": f"reference tiling, tiles sharded over {world} ranks, one all_gather, blend on every rank"}
-        del vae, y
+        del y
+        # the UNTILED decode of the same latent sharded by horizontal strips (easyanimate_b200/vae_strips.py: halo rows for the
+        # convolutions, gathered GroupNorm sums, one all_gather of the frames): no 1.81x tiling overhead, the untiled result
+        try:
+            vae.use_tiling = False
+            vae.set_tile_parallel_group(None)
+            vae.set_strip_parallel_group(world_group)
+            vae.decode(z)
+            sync_all()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            y = vae.decode(z).sample
+            e1.record()
+            sync_all()
+            (ms_s,) = max_over_ranks(e0.elapsed_time(e1))
+            if rank == 0:
+                line["vae_decode"]["strips"] = {"value": y.shape[2] * y.shape[3] * y.shape[4] / 1e6 / ms_s * 1e3, "unit": "MPix/s", "ms": ms_s,
+                                                "finite": bool(torch.isfinite(y).all()),
+                                                "mode": f"untiled decode, {world} horizontal strips (1 halo row per convolution and side, "
+                                                        "GroupNorm sums all-gathered, one all_gather of the frames)"}
+            del y
+        except Exception as e:  # a secondary line must not take the headline down
+            if rank == 0:
+                line["vae_decode"]["strips"] = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+        del vae
         torch.cuda.empty_cache()
 
     if rank == 0:

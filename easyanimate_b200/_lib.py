@@ -32,7 +32,7 @@ i64, i32, f32, vp = C.c_int64, C.c_int32, C.c_float, C.c_void_p
 # epilogues (keep in sync with include/ea_b200.h)
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RES, EPI_SCALE_F32, EPI_BIAS_RES = 0, 1, 2, 3, 4
 FRAMES_F32, FRAMES_U8 = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class GemmArgs(C.Structure):
@@ -135,12 +135,14 @@ ea_cfg_euler_step = _sig("ea_cfg_euler_step", [vp, vp, vp, vp, i64, f32, i32, f3
 ea_l1_sums = _sig("ea_l1_sums", [vp, vp, vp, i64, vp])
 ea_ew_addsub = _sig("ea_ew_addsub", [vp, vp, vp, i64, i32, vp])
 ea_dequant_e4m3 = _sig("ea_dequant_e4m3", [vp, vp, i64, vp])
+ea_ipc_open = _sig("ea_ipc_open", [vp, C.POINTER(vp)])
+ea_ipc_close = _sig("ea_ipc_close", [vp])
 ea_conv3d_causal = _sig("ea_conv3d_causal", [C.POINTER(ConvArgs), vp])
 ea_vae_prepare_latents = _sig("ea_vae_prepare_latents", [vp, vp, vp, vp, i64, i64, i64, i64, i64, f32, vp])
 ea_frames_out = _sig("ea_frames_out", [vp, vp, i64, i32, vp])
 ea_groupnorm_workspace = _sig("ea_groupnorm_workspace", [i64, i64, i64], C.c_size_t)
-ea_groupnorm_stats = _sig("ea_groupnorm_stats", [vp, vp, vp, C.c_size_t, i64, i64, i64, i64, f32, vp])
-ea_groupnorm_sums = _sig("ea_groupnorm_sums", [vp, vp, vp, C.c_size_t, i64, i64, i64, i64, vp])
+ea_groupnorm_stats = _sig("ea_groupnorm_stats", [vp, vp, vp, C.c_size_t, i64, i64, i64, i64, i64, f32, vp])
+ea_groupnorm_sums = _sig("ea_groupnorm_sums", [vp, vp, vp, C.c_size_t, i64, i64, i64, i64, i64, vp])
 ea_groupnorm_finalize = _sig("ea_groupnorm_finalize", [vp, vp, i64, i64, i64, C.c_double, f32, vp])
 ea_groupnorm_apply = _sig("ea_groupnorm_apply", [vp, vp, vp, vp, vp, i64, i64, i64, i64, i32, vp])
 ea_upsample2x = _sig("ea_upsample2x", [vp, vp, i64, i64, i64, i64, vp])

@@ -155,14 +155,15 @@ EA_DEVICE uint32_t pack_p(float lo, float hi) {
 
 // Column pairs [P0, P1) of one 32-column chunk: e = 2^(s * c - m) with packed fp32x2 arithmetic, POLY of every 4 pairs on
 // the FMA pipe (their raw scores also feed `guard`), the rest on MUFU; row-sum partials in acc2, packed bf16 pairs in pk.
-template <int POLY, int P0, int P1, bool TRUNC = false>
+// PDEN: POLY of every PDEN pairs take the polynomial (4, or 8 / 16 for a finer split between the MUFU and the FMA pipes).
+template <int POLY, int P0, int P1, bool TRUNC = false, int PDEN = 4>
 EA_DEVICE void exp_pairs(const uint32_t* s, float2 c2, float2 nm2, float2* acc2, float& guard, uint32_t* pk) {
 #pragma unroll
   for (int q = P0; q < P1; ++q) {
     const float s0 = __uint_as_float(s[2 * q]), s1 = __uint_as_float(s[2 * q + 1]);
     const float2 x = __ffma2_rn(make_float2(s0, s1), c2, nm2);
     float2 e;
-    if ((q & 3) < POLY) {
+    if ((q % PDEN) < POLY) {
       guard = fmaxf(guard, fmaxf(s0, s1));
       e = exp2_poly2(x);
     } else {
@@ -208,7 +209,7 @@ EA_DEVICE void exp_row_phased(const uint32_t* s, float2 c2, float2 nm2, float2* 
   }
 }
 
-template <int POLY, bool PHASED, bool TRUNC, int NT, int KT>
+template <int POLY, bool PHASED, bool TRUNC, int NT, int KT, int PDEN>
 __global__ void __launch_bounds__(Cfg<NT, KT>::kThreads, 1)
 attn6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
              const __grid_constant__ CUtensorMap tmap_v, const Args p) {
@@ -394,13 +395,13 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
           tmem_ld32p(tS, s);
           tmem_ld_fence(s);
           tmem_ld32p(tS + 32, s + 32);
-          exp_pairs<POLY, 0, 16, TRUNC>(s, c2, nm2, acc2, guard, pk);
+          exp_pairs<POLY, 0, 16, TRUNC, PDEN>(s, c2, nm2, acc2, guard, pk);
           tmem_ld_fence(s + 32);
           tmem_ld32p(tS + 64, s + 64);
-          exp_pairs<POLY, 0, 8, TRUNC>(s + 32, c2, nm2, acc2, guard, pk2);
+          exp_pairs<POLY, 0, 8, TRUNC, PDEN>(s + 32, c2, nm2, acc2, guard, pk2);
           tmem_ld_fence(s + 64);
           tmem_ld32p(tS + 96, s + 96);
-          exp_pairs<POLY, 8, 16, TRUNC>(s + 32, c2, nm2, acc2, guard, pk2);
+          exp_pairs<POLY, 8, 16, TRUNC, PDEN>(s + 32, c2, nm2, acc2, guard, pk2);
           tmem_ld_fence(s + 96);
           tc_fence_before();
           bar_arrive(bar_t + kSFree);  // S_t may be overwritten by QK_{j+1}
@@ -408,24 +409,24 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
           tc_fence_after();
           tmem_st16(tP, pk);
           tmem_st16(tP + 16, pk2);
-          exp_pairs<POLY, 0, 16, TRUNC>(s + 64, c2, nm2, acc2, guard, pk);
+          exp_pairs<POLY, 0, 16, TRUNC, PDEN>(s + 64, c2, nm2, acc2, guard, pk);
           tmem_st16(tP + 32, pk);
-          exp_pairs<POLY, 0, 16, TRUNC>(s + 96, c2, nm2, acc2, guard, pk2);
+          exp_pairs<POLY, 0, 16, TRUNC, PDEN>(s + 96, c2, nm2, acc2, guard, pk2);
           tmem_st16(tP + 48, pk2);
         } else {
           static_assert(KT == 64 || KT == 128, "key block of 64 or 128");
           tmem_ld32p(tS, s);
           tmem_ld_fence(s);
           tmem_ld32p(tS + 32, s + 32);
-          exp_pairs<POLY, 0, 16, TRUNC>(s, c2, nm2, acc2, guard, pk);
+          exp_pairs<POLY, 0, 16, TRUNC, PDEN>(s, c2, nm2, acc2, guard, pk);
           tmem_ld_fence(s + 32);
           tc_fence_before();
           bar_arrive(bar_t + kSFree);  // S_t may be overwritten by QK_{j+1}
-          exp_pairs<POLY, 0, 8, TRUNC>(s + 32, c2, nm2, acc2, guard, pk2);
+          exp_pairs<POLY, 0, 8, TRUNC, PDEN>(s + 32, c2, nm2, acc2, guard, pk2);
           bar_wait(bar_t + kODone, (j - 1) & 1);  // PV_{j-1} has read P_t
           tc_fence_after();
           tmem_st16(tP, pk);
-          exp_pairs<POLY, 8, 16, TRUNC>(s + 32, c2, nm2, acc2, guard, pk2);
+          exp_pairs<POLY, 8, 16, TRUNC, PDEN>(s + 32, c2, nm2, acc2, guard, pk2);
           tmem_st16(tP + 16, pk2);
         }
         const float l_blk = ((acc2[0].x + acc2[0].y) + (acc2[1].x + acc2[1].y)) + ((acc2[2].x + acc2[2].y) + (acc2[3].x + acc2[3].y));
@@ -477,7 +478,7 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
 #pragma unroll 1
         for (int c = 0; c < KT / 32; ++c) {
           // (rare path: keep it small - rotate the score registers instead of unrolling the chunks)
-          exp_pairs<POLY, 0, 16, TRUNC>(s, c2, nm2, acc2, guard, pk);
+          exp_pairs<POLY, 0, 16, TRUNC, PDEN>(s, c2, nm2, acc2, guard, pk);
           tmem_st16(tP + c * 16, pk);
 #pragma unroll
           for (int i = 0; i < KT - 32; ++i) s[i] = s[i + 32];
@@ -549,7 +550,7 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
   }
 }
 
-template <int POLY, bool PHASED, bool TRUNC, int NT = 2, int KT = 128>
+template <int POLY, bool PHASED, bool TRUNC, int NT = 2, int KT = 128, int PDEN = 4>
 static int launch(const ea_attn_args* g, cudaStream_t stream) {
   using C = Cfg<NT, KT>;
   const int64_t BH = g->B * g->H;
@@ -582,7 +583,7 @@ static int launch(const ea_attn_args* g, cudaStream_t stream) {
       p.out_text_peers[i] = reinterpret_cast<bf16*>(pe->out_text[i]);
     }
   }
-  auto kern = attn6_kernel<POLY, PHASED, TRUNC, NT, KT>;
+  auto kern = attn6_kernel<POLY, PHASED, TRUNC, NT, KT, PDEN>;
   static ::ea::PerDeviceFlag attr_flag;
   const int attr_dev = ::ea::current_device();
   if (!attr_flag.get(attr_dev)) {
@@ -604,7 +605,9 @@ int launch_attn6(const ea_attn_args* g, int poly, cudaStream_t stream) {
     switch (poly) {
       case 0: return trunc ? a6::launch<0, false, true, 3, 64>(g, stream) : a6::launch<0, false, false, 3, 64>(g, stream);
       case 1: return a6::launch<1, false, false, 3, 64>(g, stream);
-      default: return fail(EA_ERR_INVALID, "ea_attn_fwd: the 3 x 64 layout takes 0 or 1 polynomial pairs of 4");
+      case 4: return trunc ? a6::launch<1, false, true, 3, 64, 8>(g, stream) : a6::launch<1, false, false, 3, 64, 8>(g, stream);    // 1 of 8
+      case 7: return trunc ? a6::launch<1, false, true, 3, 64, 16>(g, stream) : a6::launch<1, false, false, 3, 64, 16>(g, stream);  // 1 of 16
+      default: return fail(EA_ERR_INVALID, "ea_attn_fwd: the 3 x 64 layout takes polynomial code 0, 1 (1 of 4 pairs), 4 (1 of 8) or 7 (1 of 16)");
     }
   }
   switch (poly) {

@@ -1,5 +1,7 @@
 // Library-level entry points of the C ABI: error string, version, launch counter.
 #include <atomic>
+#include <string.h>
+
 #include <string>
 
 #include "host.h"
@@ -12,7 +14,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 }  // namespace ea
 
 extern "C" const char* ea_last_error(void) { return ea::last_error_cstr(); }
-extern "C" int ea_abi_version(void) { return 3; }
+extern "C" int ea_abi_version(void) { return 4; }
 extern "C" uint64_t ea_launch_count(void) { return ea::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int ea_enable_peer_access(int32_t peer_device) {
@@ -29,5 +31,34 @@ extern "C" int ea_enable_peer_access(int32_t peer_device) {
   if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
     return ea::fail(EA_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
   (void)cudaGetLastError();
+  return EA_OK;
+}
+
+// CUDA IPC import for the sequence-parallel peer buffers.  The mapping must be made with the IMPORTING kernel's device current
+// (cudaIpcMemLazyEnablePeerAccess then sets up peer access from it to the exporting device): a mapping opened under the
+// exporter's device index - what torch's own storage sharing does - is readable by copy engines but faults when a kernel
+// of another device dereferences it (profiles/r02_debug_sp_ipc.log).
+extern "C" int ea_ipc_open(const void* handle64, void** base_out) {
+  if (!handle64 || !base_out) return ea::fail(EA_ERR_INVALID, "ea_ipc_open: null pointer");
+  cudaIpcMemHandle_t h;
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(&h, handle64, sizeof(h));
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return ea::fail(EA_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+  }
+  *base_out = p;
+  return EA_OK;
+}
+
+extern "C" int ea_ipc_close(void* base) {
+  if (!base) return EA_OK;
+  cudaError_t e = cudaIpcCloseMemHandle(base);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return ea::fail(EA_ERR_CUDA, std::string("cudaIpcCloseMemHandle: ") + cudaGetErrorString(e));
+  }
   return EA_OK;
 }

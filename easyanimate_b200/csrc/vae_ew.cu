@@ -1,6 +1,8 @@
 // HBM-bound kernels of the MagViT VAE decode: latent preparation (post_quant_conv + layout change), per-frame
 // GroupNorm statistics / apply(+SiLU), nearest spatial up-sampling, row softmax and transpose for the mid-block
 // attention, tile blending and the final clamp.  Channels-last [T,H,W,C] bf16 activations, 16-byte vector accesses.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host.h"
 #include "../../include/ea_b200.h"
@@ -40,25 +42,26 @@ __global__ void vae_prepare_latents_kernel(const bf16* __restrict__ z, const bf1
 }
 
 // ---- GroupNorm: per-frame statistics (common.py:301-305 rearranges '(b t) c h w' so every frame has its own) ----
-__global__ void gn_partial_kernel(const bf16* __restrict__ x, double* __restrict__ part, int64_t HW, int C, int G,
-                                  int pix_per_block) {
-  // Deterministic (no atomics: a decode must be reproducible bit for bit, tests/test_vae_gpu.py): every thread sums a
-  // fixed pixel subset of one 8-channel vector, the block reduces in a fixed order, one (sum, sum of squares) pair per
-  // (frame, block, group) goes to the workspace and gn_finalize_kernel adds the blocks in order.
+// Deterministic (no atomics: a decode must be reproducible bit for bit, tests/test_vae_gpu.py) AND independent of how the rows
+// of a frame are split over GPUs (strip-parallel decode, vae_strips.py): the unit of work is ONE IMAGE ROW.  A block reduces
+// one row of one frame - every thread sums a fixed pixel subset of one 8-channel vector in fp32, the block adds the threads
+// in a fixed order in fp64 - to a (sum, sum of squares) pair per group, which depends on the row's content and (W, C) only.
+// Rows are then added in fp64: a different association (rows of a strip first, then the strips) moves the sums by ~1e-16
+// relative, which disappears in the conversion of mean / rstd to fp32 except when a sum sits within that distance of an fp32
+// rounding boundary (~1e-9 per statistic) - the statistics of a strip-parallel decode are the single-GPU ones.
+__global__ void __launch_bounds__(256) gn_row_partial_kernel(const bf16* __restrict__ x, double* __restrict__ part, int rows,
+                                                             int W, int C, int G) {
   extern __shared__ float red[];  // [2][pstride][C]
-  const int t = blockIdx.y;
+  const int t = blockIdx.y, r = blockIdx.x;
   const int nvec = C >> 3;
   const int cv = threadIdx.x % nvec;
   const int prow = threadIdx.x / nvec;
   const int pstride = blockDim.x / nvec;
-  const int64_t p0 = (int64_t)blockIdx.x * pix_per_block;
-  const int64_t p1 = p0 + pix_per_block < HW ? p0 + pix_per_block : HW;
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-  const bf16* base = x + (int64_t)t * HW * C;
-  for (int64_t p = p0 + prow; p < p1; p += pstride) {
-    const uint4 u = *reinterpret_cast<const uint4*>(base + p * C + cv * 8);
+  const bf16* base = x + ((int64_t)t * rows + r) * W * C + cv * 8;
+  auto accumulate = [&](const uint4& u) {
     const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -66,7 +69,17 @@ __global__ void gn_partial_kernel(const bf16* __restrict__ x, double* __restrict
       s[2 * k] += f.x; q[2 * k] += f.x * f.x;
       s[2 * k + 1] += f.y; q[2 * k + 1] += f.y * f.y;
     }
+  };
+  // four 16-byte loads in flight per thread (the first version of this pass ran at 1.7 TB/s with one)
+  int p = prow;
+  for (; p + 3 * pstride < W; p += 4 * pstride) {
+    uint4 u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u[i] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(p + i * pstride) * C));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) accumulate(u[i]);
   }
+  for (; p < W; p += pstride) accumulate(__ldg(reinterpret_cast<const uint4*>(base + (int64_t)p * C)));
   float* rs = red + (size_t)prow * C + cv * 8;
   float* rq = red + (size_t)(pstride + prow) * C + cv * 8;
 #pragma unroll
@@ -83,39 +96,47 @@ __global__ void gn_partial_kernel(const bf16* __restrict__ x, double* __restrict
         a += (double)red[(size_t)pr * C + g * cpg + c];
         b += (double)red[(size_t)(pstride + pr) * C + g * cpg + c];
       }
-    double* dst = part + (((int64_t)t * gridDim.x + blockIdx.x) * G + g) * 2;
+    double* dst = part + (((int64_t)t * rows + r) * G + g) * 2;
     dst[0] = a;
     dst[1] = b;
   }
 }
-__global__ void gn_finalize_kernel(const double* __restrict__ part, float* __restrict__ stats, int n, int G, int blocks,
-                                   double count, float eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (frame, group)
-  if (i >= n) return;
-  const int t = i / G, g = i % G;
-  double a = 0.0, b = 0.0;
-  for (int bx = 0; bx < blocks; ++bx) {
-    const double* src = part + (((int64_t)t * blocks + bx) * G + g) * 2;
+// One warp per (frame, group): lane l adds rows l, l + 32, ... in order, the lanes are combined by a fixed shuffle tree.
+EA_DEVICE void gn_rows_sum(const double* __restrict__ part, int i, int G, int rows, double& a, double& b) {
+  const int t = i / G, g = i % G, lane = threadIdx.x & 31;
+  a = 0.0;
+  b = 0.0;
+  for (int r = lane; r < rows; r += 32) {
+    const double* src = part + (((int64_t)t * rows + r) * G + g) * 2;
     a += src[0];
     b += src[1];
   }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, off);
+    b += __shfl_xor_sync(0xffffffffu, b, off);
+  }
+}
+__global__ void gn_finalize_kernel(const double* __restrict__ part, float* __restrict__ stats, int n, int G, int rows,
+                                   double count, float eps) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // (frame, group)
+  if (i >= n) return;
+  double a, b;
+  gn_rows_sum(part, i, G, rows, a, b);
+  if ((threadIdx.x & 31) != 0) return;
   const double mean = a / count;
   double var = b / count - mean * mean;
   var = var < 0 ? 0 : var;
   stats[2 * i] = (float)mean;
   stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
-// Strip-parallel decode: the block partials of ONE rank's rows reduced to a (sum, sum of squares) pair per (frame, group) ...
-__global__ void gn_sums_kernel(const double* __restrict__ part, double* __restrict__ sums, int n, int G, int blocks) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (frame, group)
+// Strip-parallel decode: the rows of ONE rank reduced to a (sum, sum of squares) pair per (frame, group) ...
+__global__ void gn_sums_kernel(const double* __restrict__ part, double* __restrict__ sums, int n, int G, int rows) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= n) return;
-  const int t = i / G, g = i % G;
-  double a = 0.0, b = 0.0;
-  for (int bx = 0; bx < blocks; ++bx) {
-    const double* src = part + (((int64_t)t * blocks + bx) * G + g) * 2;
-    a += src[0];
-    b += src[1];
-  }
+  double a, b;
+  gn_rows_sum(part, i, G, rows, a, b);
+  if ((threadIdx.x & 31) != 0) return;
   sums[2 * i] = a;
   sums[2 * i + 1] = b;
 }
@@ -167,6 +188,68 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y
     o[k] = pack_bf16x2(v0, v1);
   }
   *reinterpret_cast<uint4*>(y + idx * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// Same arithmetic, restructured for bandwidth: a block walks a pixel range of ONE frame, a thread keeps one 8-channel vector
+// position, so mean / rstd / gamma / beta sit in registers for the whole range; four 16-byte loads in flight per thread;
+// SiLU through ex2.approx / rcp.approx (relative error 2^-21, far below the bf16 rounding that follows).
+__global__ void __launch_bounds__(256) gn_apply2_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
+                                                        const bf16* __restrict__ gamma, const bf16* __restrict__ beta,
+                                                        const float* __restrict__ stats, int64_t HW, int C, int G,
+                                                        int pix_per_block, int do_silu) {
+  const int t = blockIdx.y;
+  const int nvec = C >> 3;
+  const int cv = threadIdx.x % nvec;
+  const int prow = threadIdx.x / nvec;
+  const int pstride = blockDim.x / nvec;
+  const int cpg = C / G;
+  float mean[8], rstd[8], gm[8], bt[8];
+  {
+    const uint4 gw = __ldg(reinterpret_cast<const uint4*>(gamma) + cv);
+    const uint4 bw = __ldg(reinterpret_cast<const uint4*>(beta) + cv);
+    const uint32_t gg[4] = {gw.x, gw.y, gw.z, gw.w}, bb[4] = {bw.x, bw.y, bw.z, bw.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 gf = unpack_bf16x2(gg[k]), bf = unpack_bf16x2(bb[k]);
+      gm[2 * k] = gf.x; gm[2 * k + 1] = gf.y;
+      bt[2 * k] = bf.x; bt[2 * k + 1] = bf.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 st = __ldg(reinterpret_cast<const float2*>(stats + ((int64_t)t * G + (cv * 8 + j) / cpg) * 2));
+      mean[j] = st.x;
+      rstd[j] = st.y;
+    }
+  }
+  const int64_t p0 = (int64_t)blockIdx.x * pix_per_block;
+  const int64_t p1 = p0 + pix_per_block < HW ? p0 + pix_per_block : HW;
+  const bf16* xb = x + (int64_t)t * HW * C + cv * 8;
+  bf16* yb = y + (int64_t)t * HW * C + cv * 8;
+  auto apply = [&](const uint4& u) {
+    const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 xf = unpack_bf16x2(uw[k]);
+      float v0 = bf16_round((xf.x - mean[2 * k]) * rstd[2 * k] * gm[2 * k] + bt[2 * k]);
+      float v1 = bf16_round((xf.y - mean[2 * k + 1]) * rstd[2 * k + 1] * gm[2 * k + 1] + bt[2 * k + 1]);
+      if (do_silu) {
+        v0 = __fdividef(v0, 1.0f + __expf(-v0));
+        v1 = __fdividef(v1, 1.0f + __expf(-v1));
+      }
+      o[k] = pack_bf16x2(v0, v1);
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  int64_t p = p0 + prow;
+  for (; p + 3 * (int64_t)pstride < p1; p += 4 * (int64_t)pstride) {
+    uint4 u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u[i] = __ldg(reinterpret_cast<const uint4*>(xb + (p + (int64_t)i * pstride) * C));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(yb + (p + (int64_t)i * pstride) * C) = apply(u[i]);
+  }
+  for (; p < p1; p += pstride) *reinterpret_cast<uint4*>(yb + p * C) = apply(__ldg(reinterpret_cast<const uint4*>(xb + p * C)));
 }
 
 // nearest x2 in H and W (upsamplers.py:35,143): y[t][2h+a][2w+b][c] = x[t][h][w][c]
@@ -361,55 +444,45 @@ extern "C" int ea_vae_prepare_latents(const void* z, const void* w, const void* 
   return check_launch("vae_prepare_latents_kernel");
 }
 
-static int gn_blocks(int64_t HW) {
-  const int b = (int)((HW + 4095) / 4096);
-  return b < 1 ? 1 : b;
+extern "C" size_t ea_groupnorm_workspace(int64_t frames, int64_t rows, int64_t groups) {
+  return (size_t)frames * rows * groups * 2 * sizeof(double);
 }
 
-extern "C" size_t ea_groupnorm_workspace(int64_t frames, int64_t HW, int64_t groups) {
-  return (size_t)frames * gn_blocks(HW) * groups * 2 * sizeof(double);
+static int gn_row_partials(const char* who, const void* x, void* workspace, size_t workspace_bytes, int64_t frames, int64_t rows,
+                           int64_t W, int64_t C, int64_t groups, cudaStream_t stream) {
+  if (!(C % 8 == 0 && C % groups == 0 && C <= 2048 && 256 % (C / 8) == 0))
+    return fail(EA_ERR_INVALID, std::string(who) + ": C must be a multiple of 8 dividing into 256 threads, and of groups");
+  if (workspace_bytes < ea_groupnorm_workspace(frames, rows, groups)) return fail(EA_ERR_WORKSPACE, std::string(who) + ": workspace too small");
+  if (!(frames > 0 && rows > 0 && W > 0 && frames <= 65535 && rows < (1ll << 31) && W < (1ll << 24)))
+    return fail(EA_ERR_INVALID, std::string(who) + ": bad frame / row / width count");
+  dim3 grid((unsigned)rows, (unsigned)frames);
+  const size_t smem = 2 * (size_t)(256 / (C / 8)) * C * sizeof(float);  // 16 KB
+  gn_row_partial_kernel<<<grid, 256, smem, stream>>>((const bf16*)x, (double*)workspace, (int)rows, (int)W, (int)C, (int)groups);
+  count_launch();
+  return EA_OK;
 }
 
 extern "C" int ea_groupnorm_stats(const void* x, void* stats, void* workspace, size_t workspace_bytes, int64_t frames,
-                                  int64_t HW, int64_t C, int64_t groups, float eps, void* stream_) {
+                                  int64_t rows, int64_t W, int64_t C, int64_t groups, float eps, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   EA_REQUIRE(x && stats && workspace, "ea_groupnorm_stats: null pointer");
-  EA_REQUIRE(C % 8 == 0 && C % groups == 0 && C <= 2048 && 256 % (C / 8) == 0,
-             "ea_groupnorm_stats: C must be a multiple of 8 dividing into 256 threads, and of groups");
-  if (workspace_bytes < ea_groupnorm_workspace(frames, HW, groups))
-    return fail(EA_ERR_WORKSPACE, "ea_groupnorm_stats: workspace too small");
-  EA_REQUIRE(frames <= 65535, "ea_groupnorm_stats: too many frames");
-  const int blocks_x = gn_blocks(HW);
-  const int pix_per_block = (int)((HW + blocks_x - 1) / blocks_x);
-  dim3 grid((unsigned)blocks_x, (unsigned)frames);
-  const size_t smem = 2 * (size_t)(256 / (C / 8)) * C * sizeof(float);  // 16 KB
-  gn_partial_kernel<<<grid, 256, smem, stream>>>((const bf16*)x, (double*)workspace, HW, (int)C, (int)groups,
-                                                 pix_per_block);
-  count_launch();
+  int rc = gn_row_partials("ea_groupnorm_stats", x, workspace, workspace_bytes, frames, rows, W, C, groups, stream);
+  if (rc) return rc;
   const int n = (int)(frames * groups);
-  gn_finalize_kernel<<<(n + 127) / 128, 128, 0, stream>>>((const double*)workspace, (float*)stats, n, (int)groups,
-                                                          blocks_x, (double)HW * (double)(C / groups), eps);
+  gn_finalize_kernel<<<(n * 32 + 127) / 128, 128, 0, stream>>>((const double*)workspace, (float*)stats, n, (int)groups, (int)rows,
+                                                                (double)rows * (double)W * (double)(C / groups), eps);
   count_launch();
   return check_launch("groupnorm_stats");
 }
 
 extern "C" int ea_groupnorm_sums(const void* x, void* sums, void* workspace, size_t workspace_bytes, int64_t frames,
-                                 int64_t HW, int64_t C, int64_t groups, void* stream_) {
+                                 int64_t rows, int64_t W, int64_t C, int64_t groups, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   EA_REQUIRE(x && sums && workspace, "ea_groupnorm_sums: null pointer");
-  EA_REQUIRE(C % 8 == 0 && C % groups == 0 && C <= 2048 && 256 % (C / 8) == 0,
-             "ea_groupnorm_sums: C must be a multiple of 8 dividing into 256 threads, and of groups");
-  if (workspace_bytes < ea_groupnorm_workspace(frames, HW, groups))
-    return fail(EA_ERR_WORKSPACE, "ea_groupnorm_sums: workspace too small");
-  EA_REQUIRE(frames <= 65535, "ea_groupnorm_sums: too many frames");
-  const int blocks_x = gn_blocks(HW);
-  const int pix_per_block = (int)((HW + blocks_x - 1) / blocks_x);
-  dim3 grid((unsigned)blocks_x, (unsigned)frames);
-  const size_t smem = 2 * (size_t)(256 / (C / 8)) * C * sizeof(float);
-  gn_partial_kernel<<<grid, 256, smem, stream>>>((const bf16*)x, (double*)workspace, HW, (int)C, (int)groups, pix_per_block);
-  count_launch();
+  int rc = gn_row_partials("ea_groupnorm_sums", x, workspace, workspace_bytes, frames, rows, W, C, groups, stream);
+  if (rc) return rc;
   const int n = (int)(frames * groups);
-  gn_sums_kernel<<<(n + 127) / 128, 128, 0, stream>>>((const double*)workspace, (double*)sums, n, (int)groups, blocks_x);
+  gn_sums_kernel<<<(n * 32 + 127) / 128, 128, 0, stream>>>((const double*)workspace, (double*)sums, n, (int)groups, (int)rows);
   count_launch();
   return check_launch("groupnorm_sums");
 }
@@ -429,6 +502,17 @@ extern "C" int ea_groupnorm_apply(const void* x, void* y, const void* gamma, con
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   EA_REQUIRE(x && y && gamma && beta && stats, "ea_groupnorm_apply: null pointer");
   EA_REQUIRE(C % 8 == 0 && C % groups == 0, "ea_groupnorm_apply: bad channel count");
+  static const bool legacy = getenv("EA_GN_LEGACY_APPLY") != nullptr;  // A/B: the first (one vector per thread) kernel
+  if (!legacy && C <= 2048 && 256 % (C / 8) == 0 && frames <= 65535) {
+    // ~8 blocks per SM and frame-sized work items: 1 024 pixels per block, never fewer than one wave of blocks per call
+    int pix_per_block = 1024;
+    while (pix_per_block > 64 && frames * ((HW + pix_per_block - 1) / pix_per_block) < 4 * (int64_t)sm_count()) pix_per_block >>= 1;
+    dim3 grid((unsigned)((HW + pix_per_block - 1) / pix_per_block), (unsigned)frames);
+    gn_apply2_kernel<<<grid, 256, 0, stream>>>((const bf16*)x, (bf16*)y, (const bf16*)gamma, (const bf16*)beta,
+                                               (const float*)stats, HW, (int)C, (int)groups, pix_per_block, silu);
+    count_launch();
+    return check_launch("gn_apply2_kernel");
+  }
   const int64_t total_vec = frames * HW * (C / 8);
   gn_apply_kernel<<<(unsigned)((total_vec + 255) / 256), 256, 0, stream>>>((const bf16*)x, (bf16*)y, (const bf16*)gamma,
                                                                           (const bf16*)beta, (const float*)stats, HW,

@@ -24,6 +24,7 @@ sampler (tests/test_dist_sp_cpu.py); both forms are checked on GPUs against the 
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Callable, Optional, Tuple
 
 import torch
@@ -43,6 +44,46 @@ def all_reduce_floats(values, group) -> list:
     return [float(v) for v in t.cpu()]
 
 
+# A device allocation can be imported once per process: torch's caching allocator hands the same allocation (hence the same
+# handle) to successive exchanges, so the mappings are cached by handle and reference-counted.
+_IPC_OPEN = {}  # handle bytes -> [mapped base address, users]
+
+
+def _raw_ipc_handle(h: bytes) -> bytes:
+    """torch's shareable handle string -> the 64-byte cudaIpcMemHandle_t.  Recent torch prefixes two bytes (a version and the
+    kind: 'c' = a cudaMalloc'ed segment, 'e' = an expandable segment, which has no cudaIpcMemHandle_t)."""
+    if len(h) == 64:
+        return h
+    if len(h) == 66 and h[1:2] == b"c":
+        return h[2:]
+    raise ValueError(f"unsupported CUDA IPC handle from torch ({len(h)} bytes, kind {h[1:2]!r}): the peer-store exchange needs "
+                     "cudaMalloc'ed segments (do not enable expandable_segments), or run EA_SP_MODE=nccl")
+
+
+def _ipc_open(handle: bytes) -> int:
+    from . import _lib as L
+    ent = _IPC_OPEN.get(handle)
+    if ent is None:
+        mapped = L.vp()
+        if len(handle) != 64:
+            raise ValueError(f"a cudaIpcMemHandle_t is 64 bytes, got {len(handle)}")
+        L.check(L.ea_ipc_open((C.c_char * 64).from_buffer_copy(handle), C.byref(mapped)), "ea_ipc_open")
+        ent = _IPC_OPEN[handle] = [mapped.value, 0]
+    ent[1] += 1
+    return ent[0]
+
+
+def _ipc_close(handle: bytes) -> None:
+    from . import _lib as L
+    ent = _IPC_OPEN.get(handle)
+    if ent is None:
+        return
+    ent[1] -= 1
+    if ent[1] <= 0:
+        del _IPC_OPEN[handle]
+        L.check(L.ea_ipc_close(ent[0]), "ea_ipc_close")
+
+
 class PeerExchange:
     """Symmetric q/k/v and attention-output buffers of one (B, H, S_t, S_loc) problem, mapped into every rank of the group,
     and the pointer tables the fused kernels take.  Built once per shape and reused by every block of every step."""
@@ -58,30 +99,37 @@ class PeerExchange:
         self.B, self.H, self.Hl, self.S_t, self.S_loc = B, H, H // P, S_t, S_loc
         S = S_t + P * S_loc
         bf16 = torch.bfloat16
-        # one allocation per buffer (a CUDA IPC handle names a whole allocation + offset; torch's storage sharing does both)
-        self.q = torch.empty((B, self.Hl, S, 64), device=device, dtype=bf16)
-        self.k = torch.empty_like(self.q)
-        self.v = torch.empty_like(self.q)
-        self.out_video = torch.empty((B, S_loc, H * 64), device=device, dtype=bf16)
-        self.out_text = torch.empty((B, S_t, H * 64), device=device, dtype=bf16)
+        # ONE allocation for the five buffers: a CUDA IPC handle names a whole device allocation, so every peer opens one handle
+        n_qkv = B * self.Hl * S * 64
+        sizes = [n_qkv, n_qkv, n_qkv, B * S_loc * H * 64, B * S_t * H * 64]
+        offs = [0]
+        for n in sizes:
+            offs.append(offs[-1] + (n * 2 + 1023) // 1024 * 1024)  # byte offsets, 1 KB aligned
+        self._buf = torch.empty((offs[-1],), device=device, dtype=torch.uint8)
+
+        def part(i, shape):
+            return self._buf[offs[i]:offs[i] + sizes[i] * 2].view(bf16).view(shape)
+        self.q, self.k, self.v = (part(i, (B, self.Hl, S, 64)) for i in range(3))
+        self.out_video = part(3, (B, S_loc, H * 64))
+        self.out_text = part(4, (B, S_t, H * 64))
         self._flag = torch.zeros((1,), device=device, dtype=torch.int32)
-        mine = [self.q, self.k, self.v, self.out_video, self.out_text]
-        handles = [t.untyped_storage()._share_cuda_() + (t.storage_offset() * t.element_size(),) for t in mine]
+        # export: the allocation's cudaIpcMemHandle_t and this buffer's byte offset inside it (torch's storage sharing looks both
+        # up in its caching allocator).  The peers do NOT import through torch - it would open the mapping under the exporter's
+        # device index, which a kernel of another device cannot dereference - but through ea_ipc_open on their own device.
+        share = self._buf.untyped_storage()._share_cuda_()
+        handle, base_off = _raw_ipc_handle(bytes(share[1])), int(share[3]) + self._buf.storage_offset()
         gathered = [None] * P
-        dist.all_gather_object(gathered, (torch.cuda.current_device(), handles), group=group)
-        self._peer_storages = []  # keep the mappings alive
+        dist.all_gather_object(gathered, (torch.cuda.current_device(), handle, base_off), group=group)
+        self._opened = []  # mapped bases, closed by release()
         ptrs = []
-        for r, (peer_dev, hs) in enumerate(gathered):
+        for r, (peer_dev, hnd, off) in enumerate(gathered):
             if r == self.rank:
-                ptrs.append([t.data_ptr() for t in mine])
-                continue
-            L.check(L.ea_enable_peer_access(int(peer_dev)), "ea_enable_peer_access")
-            row = []
-            for h in hs:
-                st = torch.UntypedStorage._new_shared_cuda(*h[:8])
-                self._peer_storages.append(st)
-                row.append(st.data_ptr() + h[8])
-            ptrs.append(row)
+                base = self._buf.data_ptr()
+            else:
+                L.check(L.ea_enable_peer_access(int(peer_dev)), "ea_enable_peer_access")
+                base = _ipc_open(hnd) + off
+                self._opened.append(hnd)
+            ptrs.append([base + offs[i] for i in range(5)])
         self.qkv_video, self.qkv_text, self.attn = L.QkvPeers(), L.QkvPeers(), L.AttnPeers()
         self.qkv_video.heads_per_peer = self.qkv_text.heads_per_peer = self.Hl
         for r in range(P):
@@ -91,6 +139,17 @@ class PeerExchange:
         self.qkv_text.q[self.rank], self.qkv_text.k[self.rank], self.qkv_text.v[self.rank] = ptrs[self.rank][:3]
         self.attn.n_peers, self.attn.tokens_per_peer, self.attn.out_heads, self.attn.head0 = P, S_loc, H, self.rank * self.Hl
         dist.barrier(group=group)  # nobody stores into a peer before every mapping exists
+
+    def release(self):
+        """Unmap the peers' buffers (every rank, collectively, before the buffers are freed or replaced)."""
+        from . import _lib as L
+        if self._opened:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)  # nobody is still storing into a buffer that is about to be unmapped
+            for hnd in self._opened:
+                _ipc_close(hnd)
+            self._opened = []
+            dist.barrier(group=self.group)
 
     def barrier(self):
         """Orders the kernels of different GPUs on the compute stream (no host synchronisation): the 4-byte all-reduce can
@@ -113,8 +172,16 @@ class UlyssesAttention:
     def exchange(self, B: int, H: int, S_t: int, S_loc: int, device) -> PeerExchange:
         key = (B, H, S_t, S_loc, str(device))
         if key not in self._px:
-            self._px = {key: PeerExchange(self.group, B, H, S_t, S_loc, device)}  # one shape at a time: free the previous buffers
+            for old in self._px.values():  # one shape at a time: unmap and free the previous buffers
+                old.release()
+            self._px = {key: PeerExchange(self.group, B, H, S_t, S_loc, device)}
         return self._px[key]
+
+    def release(self):
+        """Unmap and drop the peer-store buffers (collective over the group); the next forward builds new ones."""
+        for px in self._px.values():
+            px.release()
+        self._px = {}
 
     # ---- token sharding of the per-token streams ----------------------------------------------------------------
     def local_range(self, S_v: int) -> Tuple[int, int]:

@@ -205,6 +205,22 @@ class TeaCache:
         self.previous_residual = None
 
 
+def sincos_pos_embed_2d(embed_dim: int, grid_size, base_size: int = 16):
+    """diffusers 0.30/0.31 `get_2d_sincos_pos_embed(embed_dim, (H, W))`, which the reference calls for the Control model's
+    `ref_pos_embedding` buffer (transformer3d.py:1424), restated from its published (MAE) algorithm: numpy float64
+    [H*W, embed_dim], rows in (h, w) order, columns (sin | cos) of the h axis then of the w axis."""
+    import numpy as np
+
+    def one_d(dim, pos):
+        omega = 1.0 / 10000 ** (np.arange(dim // 2, dtype=np.float64) / (dim / 2.0))
+        out = np.einsum("m,d->md", pos.reshape(-1), omega)
+        return np.concatenate([np.sin(out), np.cos(out)], axis=1)
+    grid_h = np.arange(grid_size[0], dtype=np.float32) / (grid_size[0] / base_size)
+    grid_w = np.arange(grid_size[1], dtype=np.float32) / (grid_size[1] / base_size)
+    grid = np.stack(np.meshgrid(grid_w, grid_h), axis=0).reshape([2, 1, grid_size[1], grid_size[0]])
+    return np.concatenate([one_d(embed_dim // 2, grid[0]), one_d(embed_dim // 2, grid[1])], axis=1)
+
+
 class _Fp8Staging:
     """bf16 staging for a model whose parameters are STORED as float8_e4m3fn - the reference's `model_cpu_offload_and_qfloat8`
     mode (predict_t2v.py:37,106: from_pretrained_2d(torch_dtype=float8_e4m3fn); utils/fp8_optimization.py:6-35 casts every
@@ -317,9 +333,8 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
             raise ValueError("easyanimate_b200 patch-embed kernels are built for patch_size=2 (all v5/v5.1 releases)")
         if activation_fn != "gelu-approximate" or timestep_activation_fn != "silu":
             raise ValueError("only activation_fn='gelu-approximate' / timestep_activation_fn='silu' are implemented")
-        if swa_layers is not None or after_norm or ref_channels is not None or clip_channels is not None:
-            raise NotImplementedError("swa_layers / after_norm / ref_channels / clip_channels branches are outside the "
-                                      "v5.1 T2V/I2V hot path (SURVEY.md §8 out-of-scope rows)")
+        if swa_layers is not None or after_norm:
+            raise NotImplementedError("swa_layers / after_norm are not used by the v5.1 T2V / I2V / Control models")
         if not norm_elementwise_affine:
             raise NotImplementedError("norm_elementwise_affine=False is not used by any released config")
         self.num_heads = num_attention_heads
@@ -342,6 +357,12 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
             if text_embed_dim_t5 is not None:
                 # (the reference sizes this RMSNorm with text_embed_dim, transformer3d.py:1415-1418)
                 self.text_proj_t5 = nn.Sequential(_RMSNormParams(text_embed_dim), nn.Linear(text_embed_dim_t5, d))
+        if ref_channels is not None:  # v5.1 Control: reference-image tokens (transformer3d.py:1420-1426)
+            self.ref_proj = nn.Conv2d(ref_channels, d, kernel_size=(patch_size, patch_size), stride=patch_size, bias=True)
+            self.register_buffer("ref_pos_embedding", torch.from_numpy(
+                sincos_pos_embed_2d(d, (self.post_patch_height, self.post_patch_width))), persistent=False)
+        if clip_channels is not None:  # transformer3d.py:1428-1429
+            self.clip_proj = nn.Linear(clip_channels, d)
         self.transformer_blocks = nn.ModuleList([
             EasyAnimateDiTBlock(d, num_attention_heads, attention_head_dim, time_embed_dim, norm_elementwise_affine,
                                 norm_eps, is_mmdit_block=i < mmdit_layers) for i in range(num_layers)])
@@ -352,7 +373,8 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
         self.sequence_parallel = None  # UlyssesAttention, see set_sequence_parallel_group
         self.cfg_parallel_group = None  # 2-rank group holding the other CFG branch, see set_cfg_parallel_group
         self.gradient_checkpointing = False
-        self._proj_w_cache: Optional[tuple] = None
+        self._proj_w_cache: Dict[str, tuple] = {}
+        self._ref_pos_cache: Optional[tuple] = None
         self._fp8: Optional[tuple] = None  # (parameter key, _Fp8Staging) when the parameters are stored as float8_e4m3fn
 
     # ----------------------------------------------------------------------------------------------------------
@@ -368,6 +390,9 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
         gets the full output; video tokens and attention heads must divide by the group size.  None restores
         single-GPU execution."""
         from .sequence_parallel import UlyssesAttention
+        old = getattr(self, "sequence_parallel", None)
+        if old is not None:
+            old.release()  # collective: every rank of the old group unmaps its peers' buffers
         self.sequence_parallel = None if group is None else UlyssesAttention(group)
 
     def set_cfg_parallel_group(self, group):
@@ -386,15 +411,30 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
             self._fp8 = (key, _Fp8Staging(self))
         return self._fp8[1]
 
-    def _patch_weight(self, ldk: int) -> torch.Tensor:
-        w = self.proj.weight
+    def _patch_weight(self, ldk: int, which: str = "proj") -> torch.Tensor:
+        """The 2x2 patch-embed Conv2d weight of `proj` / `ref_proj` as the [d, ldk] GEMM operand of ea_patchify's rows."""
+        w = getattr(self, which).weight
         key = ops.param_key(w) + (ldk,)
-        if self._proj_w_cache is None or self._proj_w_cache[0] != key:
+        ent = self._proj_w_cache.get(which)
+        if ent is None or ent[0] != key:
             w2 = w.detach().reshape(w.shape[0], -1)  # [d, C*4], K index = c*4 + ph*2 + pw
             if w2.shape[1] != ldk:
                 w2 = torch.nn.functional.pad(w2, (0, ldk - w2.shape[1]))
-            self._proj_w_cache = (key, w2.contiguous())
-        return self._proj_w_cache[1]
+            ent = self._proj_w_cache[which] = (key, w2.contiguous())
+        return ent[1]
+
+    def _ref_pos_table(self, gh: int, gw: int) -> torch.Tensor:
+        """transformer3d.py:1546-1553: the 2-D sin-cos table of the (post_patch_height x post_patch_width) training grid resized
+        to this call's patch grid with F.interpolate(trilinear) -> [gh*gw, d] in the buffer's dtype.  A table like the RoPE
+        one: depends on the grid size only, built once per size with the reference's own torch call and cached."""
+        buf = self.ref_pos_embedding
+        key = (gh, gw, buf.data_ptr(), buf.dtype)
+        if self._ref_pos_cache is None or self._ref_pos_cache[0] != key:
+            emb = buf.shape[-1]
+            pe = buf.view(1, 1, self.post_patch_height, self.post_patch_width, emb).permute([0, 4, 1, 2, 3])
+            pe = torch.nn.functional.interpolate(pe, size=[1, gh, gw], mode="trilinear", align_corners=False)
+            self._ref_pos_cache = (key, pe.permute([0, 2, 3, 4, 1]).reshape(gh * gw, emb).contiguous())
+        return self._ref_pos_cache[1]
 
     def _text_tokens(self, seq, enc: torch.Tensor) -> torch.Tensor:
         B, S_t, E = enc.shape
@@ -433,9 +473,10 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
                             "weights as torch.float8_e4m3fn: they are expanded to bf16 block by block)")
         staging = self._fp8_staging() if fp8 else None
         P = staging.head if fp8 else self  # owner of the non-block parameters the kernels read
-        if ref_latents is not None or clip_encoder_hidden_states is not None or timestep_cond is not None:
-            raise NotImplementedError("ref_latents / clip_encoder_hidden_states / timestep_cond are outside the v5.1 "
-                                      "T2V/I2V hot path")
+        if timestep_cond is not None:
+            raise NotImplementedError("timestep_cond is not used by any v5.1 pipeline (TimestepEmbedding is built without cond_proj)")
+        if clip_encoder_hidden_states is not None and ref_latents is None:
+            raise ValueError("clip_encoder_hidden_states needs ref_latents (the reference concatenates the two, transformer3d.py:1561)")
         B, C, F, H, W = hidden_states.shape
         d, p = self.inner_dim, self.patch_size
         dev = hidden_states.device
@@ -465,6 +506,22 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
             S_t5 = encoder_hidden_states_t5.shape[1]
             x_t = torch.cat([x_t.view(B, S_t, d), x_t5.view(B, S_t5, d)], dim=1).reshape(B * (S_t + S_t5), d).contiguous()
             S_t += S_t5
+
+        # 3b. v5.1 Control: reference-image tokens REPLACE the text tokens, CLIP tokens go in front (transformer3d.py:1538-1561)
+        if ref_latents is not None:
+            if ref_latents.shape[2] != 1 or tuple(ref_latents.shape[3:]) != (H, W):
+                raise ValueError("ref_latents must be one latent frame of the video's size (the reference adds a [1, h*w, d] "
+                                 "position table to them, transformer3d.py:1554)")
+            ar = ops.patchify(ref_latents.to(bf16))
+            r = ops.gemm(ar, P._patch_weight(ar.shape[1], "ref_proj"), P.ref_proj.bias)  # [B*hw, d]
+            pe = P._ref_pos_table(H // p, W // p).to(bf16)
+            x_t = ops.ew_add(r, pe.unsqueeze(0).expand(B, -1, -1).reshape(r.shape).contiguous())
+            S_t = (H // p) * (W // p)
+            if clip_encoder_hidden_states is not None:
+                S_c = clip_encoder_hidden_states.shape[1]
+                c = ops.gemm(clip_encoder_hidden_states.to(bf16).reshape(B * S_c, -1).contiguous(), P.clip_proj.weight, P.clip_proj.bias)
+                x_t = torch.cat([c.view(B, S_c, d), x_t.view(B, S_t, d)], dim=1).reshape(B * (S_c + S_t), d).contiguous()
+                S_t += S_c
 
         rope = None
         if image_rotary_emb is not None:

@@ -84,9 +84,9 @@ def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: 
     T, H, W, Cc = x.shape
     assert x.is_contiguous()
     stats = torch.empty((T, groups, 2), device=x.device, dtype=torch.float32)
-    ws_bytes = L.ea_groupnorm_workspace(T, H * W, groups)
+    ws_bytes = L.ea_groupnorm_workspace(T, H, groups)
     ws = torch.empty((ws_bytes,), device=x.device, dtype=torch.uint8)
-    L.check(L.ea_groupnorm_stats(_p(x), _p(stats), _p(ws), ws_bytes, T, H * W, Cc, groups, eps, _stream()),
+    L.check(L.ea_groupnorm_stats(_p(x), _p(stats), _p(ws), ws_bytes, T, H, W, Cc, groups, eps, _stream()),
             "ea_groupnorm_stats")
     y = torch.empty_like(x)
     L.check(L.ea_groupnorm_apply(_p(x), _p(y), _p(gamma), _p(beta), _p(stats), T, H * W, Cc, groups, int(silu),
@@ -100,9 +100,9 @@ def groupnorm_sums(x: torch.Tensor, groups: int) -> torch.Tensor:
     T, H, W, Cc = x.shape
     assert x.is_contiguous()
     sums = torch.empty((T, groups, 2), device=x.device, dtype=torch.float64)
-    ws_bytes = L.ea_groupnorm_workspace(T, H * W, groups)
+    ws_bytes = L.ea_groupnorm_workspace(T, H, groups)
     ws = torch.empty((ws_bytes,), device=x.device, dtype=torch.uint8)
-    L.check(L.ea_groupnorm_sums(_p(x), _p(sums), _p(ws), ws_bytes, T, H * W, Cc, groups, _stream()), "ea_groupnorm_sums")
+    L.check(L.ea_groupnorm_sums(_p(x), _p(sums), _p(ws), ws_bytes, T, H, W, Cc, groups, _stream()), "ea_groupnorm_sums")
     return sums
 
 

@@ -237,6 +237,12 @@ int ea_attn_generations(void);
  * device may then dereference pointers into `peer_device`'s memory (ea_qkv_peers / ea_attn_peers buffers). */
 int ea_enable_peer_access(int32_t peer_device);
 
+/* Import a peer process's device allocation (a 64-byte cudaIpcMemHandle_t of its base) into the CURRENT device's context so
+ * that kernels launched on the current device may store into it (cudaIpcOpenMemHandle with lazy peer access); base_out is
+ * the mapped base address.  One open per handle and process; ea_ipc_close unmaps. */
+int ea_ipc_open(const void* handle64, void** base_out);
+int ea_ipc_close(void* base);
+
 /* ------------------------------------------------------------------------------------------------------------
  * MagViT VAE decode (AutoencoderKLMagvit.decode, autoencoder_magvit.py:271-317,381-448; Decoder,
  * omnigen_enc_dec.py:555-677).  Activations are channels-last [T,H,W,C] bf16 for one batch element.
@@ -289,19 +295,21 @@ int ea_vae_prepare_latents(const void* z, const void* w, const void* bias, void*
 enum { EA_FRAMES_F32 = 0, EA_FRAMES_U8 = 1 };
 int ea_frames_out(const void* x, void* out, int64_t n, int32_t out_kind, void* stream);
 
-/* Per-frame GroupNorm (common.py:301-319 with set_3dgroupnorm; omnigen_enc_dec.py:603-609):
- * stats[frames,groups,2] = (mean, rstd) fp32; workspace = ea_groupnorm_workspace() bytes of scratch. */
-size_t ea_groupnorm_workspace(int64_t frames, int64_t HW, int64_t groups);
-int ea_groupnorm_stats(const void* x, void* stats, void* workspace, size_t workspace_bytes, int64_t frames, int64_t HW,
-                       int64_t C, int64_t groups, float eps, void* stream);
+/* Per-frame GroupNorm (common.py:301-319 with set_3dgroupnorm; omnigen_enc_dec.py:603-609) of x [frames, rows, W, C]:
+ * stats[frames,groups,2] = (mean, rstd) fp32; workspace = ea_groupnorm_workspace() bytes of scratch.  The statistics are
+ * accumulated per image row and the rows added in fp64, so they do not depend on how a frame's rows are split over GPUs. */
+size_t ea_groupnorm_workspace(int64_t frames, int64_t rows, int64_t groups);
+int ea_groupnorm_stats(const void* x, void* stats, void* workspace, size_t workspace_bytes, int64_t frames, int64_t rows,
+                       int64_t W, int64_t C, int64_t groups, float eps, void* stream);
 /* y = [SiLU](bf16((x-mean)*rstd*gamma+beta)) */
 /* Strip-parallel decode (one frame sequence split into row strips over several GPUs): the per-frame
  * GroupNorm statistics are global, so each GPU reduces ITS rows to (sum, sum of squares) per (frame, group) in fp64
  * [frames, groups, 2] (ea_groupnorm_sums; workspace as ea_groupnorm_stats), the pairs of all GPUs are gathered
  * [parts, frames, groups, 2] and added in rank order into the same mean / rstd on every GPU (ea_groupnorm_finalize; count =
- * pixels of the WHOLE frame x channels per group).  With parts = 1 the result equals ea_groupnorm_stats. */
-int ea_groupnorm_sums(const void* x, void* sums, void* workspace, size_t workspace_bytes, int64_t frames, int64_t HW, int64_t C,
-                      int64_t groups, void* stream);
+ * pixels of the WHOLE frame x channels per group).  With parts = 1 the result equals ea_groupnorm_stats; with more parts
+ * too: the per-row partial sums are the same and the fp64 association differences (~1e-16) vanish in the fp32 result. */
+int ea_groupnorm_sums(const void* x, void* sums, void* workspace, size_t workspace_bytes, int64_t frames, int64_t rows, int64_t W,
+                      int64_t C, int64_t groups, void* stream);
 int ea_groupnorm_finalize(const void* sums, void* stats, int64_t parts, int64_t frames, int64_t groups, double count, float eps,
                           void* stream);
 int ea_groupnorm_apply(const void* x, void* y, const void* gamma, const void* beta, const void* stats, int64_t frames,

@@ -65,8 +65,37 @@ CombinedTimestepLabelEmbeddings = placeholder("CombinedTimestepLabelEmbeddings")
 PixArtAlphaCombinedTimestepSizeEmbeddings = placeholder("PixArtAlphaCombinedTimestepSizeEmbeddings")
 
 
-def get_2d_sincos_pos_embed(*a, **k):
-    raise NotImplementedError("diffusers shim: get_2d_sincos_pos_embed is not on the EasyAnimateV5.1 path")
+def get_1d_sincos_pos_embed_from_grid(embed_dim, pos):
+    """diffusers 0.30/0.31 embeddings.get_1d_sincos_pos_embed_from_grid (MAE): [M] positions -> [M, embed_dim] (sin | cos)."""
+    import numpy as np
+    omega = np.arange(embed_dim // 2, dtype=np.float64)
+    omega /= embed_dim / 2.0
+    omega = 1.0 / 10000 ** omega
+    out = np.einsum("m,d->md", pos.reshape(-1), omega)
+    return np.concatenate([np.sin(out), np.cos(out)], axis=1)
+
+
+def get_2d_sincos_pos_embed_from_grid(embed_dim, grid):
+    import numpy as np
+    emb_h = get_1d_sincos_pos_embed_from_grid(embed_dim // 2, grid[0])
+    emb_w = get_1d_sincos_pos_embed_from_grid(embed_dim // 2, grid[1])
+    return np.concatenate([emb_h, emb_w], axis=1)
+
+
+def get_2d_sincos_pos_embed(embed_dim, grid_size, cls_token=False, extra_tokens=0, interpolation_scale=1.0, base_size=16):
+    """diffusers 0.30/0.31 embeddings.get_2d_sincos_pos_embed restated from its published algorithm (the reference calls it
+    with (inner_dim, (post_patch_height, post_patch_width)), transformer3d.py:1424): numpy float64 [H*W, embed_dim]."""
+    import numpy as np
+    if isinstance(grid_size, int):
+        grid_size = (grid_size, grid_size)
+    grid_h = np.arange(grid_size[0], dtype=np.float32) / (grid_size[0] / base_size) / interpolation_scale
+    grid_w = np.arange(grid_size[1], dtype=np.float32) / (grid_size[1] / base_size) / interpolation_scale
+    grid = np.meshgrid(grid_w, grid_h)  # w goes first
+    grid = np.stack(grid, axis=0).reshape([2, 1, grid_size[1], grid_size[0]])
+    pos_embed = get_2d_sincos_pos_embed_from_grid(embed_dim, grid)
+    if cls_token and extra_tokens > 0:
+        pos_embed = np.concatenate([np.zeros([extra_tokens, embed_dim]), pos_embed], axis=0)
+    return pos_embed
 
 
 def get_3d_sincos_pos_embed(*a, **k):

@@ -302,12 +302,27 @@ class OracleTeaCache:
         self.previous_residual = None
 
 
+def sincos_pos_embed_2d(embed_dim, grid_size, base_size=16):
+    """diffusers 0.30/0.31 `get_2d_sincos_pos_embed(embed_dim, (H, W))` restated from its published algorithm (third-party,
+    unpinned - DESIGN.md section 4): numpy float64 [H*W, embed_dim]."""
+    def one_d(dim, pos):
+        omega = 1.0 / 10000 ** (np.arange(dim // 2, dtype=np.float64) / (dim / 2.0))
+        out = np.einsum("m,d->md", pos.reshape(-1), omega)
+        return np.concatenate([np.sin(out), np.cos(out)], axis=1)
+    grid_h = np.arange(grid_size[0], dtype=np.float32) / (grid_size[0] / base_size)
+    grid_w = np.arange(grid_size[1], dtype=np.float32) / (grid_size[1] / base_size)
+    grid = np.stack(np.meshgrid(grid_w, grid_h), axis=0).reshape([2, 1, grid_size[1], grid_size[0]])
+    return np.concatenate([one_d(embed_dim // 2, grid[0]), one_d(embed_dim // 2, grid[1])], axis=1)
+
+
 class OracleTransformer3D(nn.Module):
-    """transformer3d.py:1346-1689, v5.1 configuration space (no ref/clip/control branches, no TeaCache)."""
+    """transformer3d.py:1346-1689, v5.1 configuration space incl. the control model's ref / clip token branches
+    (transformer3d.py:1420-1429,1538-1561); TeaCache via `teacache`."""
 
     def __init__(self, num_attention_heads=30, attention_head_dim=64, in_channels=16, out_channels=16, patch_size=2,
                  num_layers=30, mmdit_layers=10000, time_embed_dim=512, add_norm_text_encoder=True, text_embed_dim=3584,
-                 text_embed_dim_t5=None, norm_eps=1e-5, flip_sin_to_cos=True, freq_shift=0, **unused):
+                 text_embed_dim_t5=None, norm_eps=1e-5, flip_sin_to_cos=True, freq_shift=0, sample_width=90, sample_height=60,
+                 ref_channels=None, clip_channels=None, **unused):
         super().__init__()
         self.cfg = dict(num_attention_heads=num_attention_heads, attention_head_dim=attention_head_dim,
                         in_channels=in_channels, out_channels=out_channels, patch_size=patch_size, num_layers=num_layers,
@@ -331,12 +346,20 @@ class OracleTransformer3D(nn.Module):
         self.transformer_blocks = nn.ModuleList([
             EasyAnimateDiTBlock(d, num_attention_heads, attention_head_dim, time_embed_dim, norm_eps,
                                 is_mmdit_block=i < mmdit_layers) for i in range(num_layers)])
+        self.post_patch_height, self.post_patch_width = sample_height // patch_size, sample_width // patch_size
+        if ref_channels is not None:  # transformer3d.py:1420-1426
+            self.ref_proj = nn.Conv2d(ref_channels, d, kernel_size=(patch_size, patch_size), stride=patch_size, bias=True)
+            self.register_buffer("ref_pos_embedding", torch.from_numpy(
+                sincos_pos_embed_2d(d, (self.post_patch_height, self.post_patch_width))), persistent=False)
+        if clip_channels is not None:  # transformer3d.py:1428-1429
+            self.clip_proj = nn.Linear(clip_channels, d)
         self.norm_final = nn.LayerNorm(d, norm_eps, True)
         self.norm_out = AdaLayerNorm(time_embed_dim, 2 * d, norm_eps)
         self.proj_out = nn.Linear(d, patch_size * patch_size * out_channels)
 
     def forward(self, hidden_states, timestep, encoder_hidden_states=None, encoder_hidden_states_t5=None,
-                image_rotary_emb=None, inpaint_latents=None, control_latents=None, **ignored):
+                image_rotary_emb=None, inpaint_latents=None, control_latents=None, ref_latents=None,
+                clip_encoder_hidden_states=None, **ignored):
         batch_size, channels, video_length, height, width = hidden_states.size()
         p = self.patch_size
         temb = get_timestep_embedding(timestep, self.inner_dim, self.flip_sin_to_cos, self.freq_shift)
@@ -353,6 +376,19 @@ class OracleTransformer3D(nn.Module):
         if encoder_hidden_states_t5 is not None:
             encoder_hidden_states_t5 = self.text_proj_t5(encoder_hidden_states_t5)
             encoder_hidden_states = torch.cat([encoder_hidden_states, encoder_hidden_states_t5], dim=1).contiguous()
+        if ref_latents is not None:  # transformer3d.py:1538-1556: the reference-image tokens REPLACE the text tokens
+            rb, rc, rf, rh, rw = ref_latents.shape
+            r = self.ref_proj(ref_latents.permute(0, 2, 1, 3, 4).flatten(0, 1))
+            r = r.unflatten(0, (rb, rf)).permute(0, 2, 1, 3, 4).flatten(2).transpose(1, 2)  # [b, f*h*w, d]
+            emb = hidden_states.size()[-1]
+            pe = self.ref_pos_embedding.view(1, 1, self.post_patch_height, self.post_patch_width, emb).permute([0, 4, 1, 2, 3])
+            pe = F.interpolate(pe, size=[1, height // p, width // p], mode="trilinear", align_corners=False)
+            pe = pe.permute([0, 2, 3, 4, 1]).view(1, -1, emb)
+            ref_latents = r + pe
+            encoder_hidden_states = ref_latents
+        if clip_encoder_hidden_states is not None:  # transformer3d.py:1558-1561
+            clip_encoder_hidden_states = self.clip_proj(clip_encoder_hidden_states)
+            encoder_hidden_states = torch.concat([clip_encoder_hidden_states, ref_latents], dim=1)
         # TeaCache (transformer3d.py:1563-1636)
         tc = getattr(self, "teacache", None)
         should_calc = True

@@ -114,6 +114,9 @@ DIT_REF_CASES = {
 }
 
 
+CONTROL_REF_OVER = dict(ref_channels=16, clip_channels=96, sample_width=20, sample_height=12)
+
+
 def _dit_inputs(cfg, shape, seed, inpaint_c):
     B, F, H, W, St = shape
     g = torch.Generator().manual_seed(seed + 100)
@@ -140,6 +143,27 @@ def make_dit_reference():
                   metadata={"source": "reference EasyAnimateTransformer3DModel (fp32, CPU, diffusers primitives from oracle/_refshim)",
                             "seed": str(seed), "config": repr(cfg), "shape": repr(shape)})
         print(name, tuple(out.shape), float(out.std()))
+    # v5.1 Control with a reference image and CLIP tokens (transformer3d.py:1420-1429,1538-1561); fp32 modules (the float64
+    # position-table buffer follows .to(float32) like it follows .to(bfloat16) in the pipelines)
+    cfg, seed = {**DIT_CFG, **CONTROL_REF_OVER}, 25
+    ref = ref_dit.reference_transformer(**cfg).eval().to(torch.float32)
+    ref.load_state_dict(dit.init_weights_(dit.OracleTransformer3D(**cfg), seed).state_dict(), strict=True)
+    t = _dit_inputs(cfg, (2, 2, 8, 12, 9), seed, 0)
+    g = torch.Generator().manual_seed(seed + 200)
+    t["ref_latents"] = torch.randn(2, cfg["ref_channels"], 1, 8, 12, generator=g)
+    t["clip_encoder_hidden_states"] = torch.randn(2, 5, cfg["clip_channels"], generator=g)
+    rope = dit.rope_for_video(64, 96, 2)
+    with torch.no_grad():
+        out = ref(t["latents"], t["timestep"], encoder_hidden_states=t["encoder_hidden_states"], image_rotary_emb=rope,
+                  ref_latents=t["ref_latents"], clip_encoder_hidden_states=t["clip_encoder_hidden_states"], return_dict=False)[0]
+        out_ref_only = ref(t["latents"], t["timestep"], encoder_hidden_states=t["encoder_hidden_states"], image_rotary_emb=rope,
+                           ref_latents=t["ref_latents"], return_dict=False)[0]
+    t["out"], t["out_ref_only"] = out.contiguous(), out_ref_only.contiguous()
+    save_file(t, os.path.join(HERE, "dit_ref_control_ref_clip.safetensors"),
+              metadata={"source": "reference EasyAnimateTransformer3DModel with ref_channels / clip_channels (fp32, CPU, diffusers "
+                                  "primitives incl. get_2d_sincos_pos_embed from oracle/_refshim)", "seed": str(seed),
+                        "config": repr(cfg), "shape": repr((2, 2, 8, 12, 9))})
+    print("dit_ref_control_ref_clip", tuple(out.shape), float(out.std()))
     # TeaCache: 6 calls with slowly drifting inputs; record every output and which calls were skipped
     cfg, seed = DIT_CFG, 24
     ref = ref_dit.reference_transformer(**cfg).eval()

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/ea_b200.h but not exported"
     lib.ea_abi_version.restype = ctypes.c_int
     from easyanimate_b200 import _lib as L
-    assert lib.ea_abi_version() == L.ABI_VERSION == 3
+    assert lib.ea_abi_version() == L.ABI_VERSION == 4
     lib.ea_last_error.restype = ctypes.c_char_p
     assert isinstance(lib.ea_last_error(), bytes)
 

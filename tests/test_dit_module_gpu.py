@@ -11,7 +11,7 @@ bf16 = torch.bfloat16
 def _build(cfg, seed=1234, device="cuda"):
     from oracle import dit
     from easyanimate_b200.transformer3d import EasyAnimateTransformer3DModel
-    o32 = dit.init_weights_(dit.OracleTransformer3D(**cfg), seed)
+    o32 = dit.init_weights_(dit.OracleTransformer3D(**cfg), seed).to(torch.float32)  # (.to: the float64 ref_pos_embedding buffer)
     ob = dit.OracleTransformer3D(**cfg).to(bf16)
     ob.load_state_dict({k: v.to(bf16) for k, v in o32.state_dict().items()})
     o32.load_state_dict({k: v.float() for k, v in ob.state_dict().items()})  # truth uses the bf16-rounded weights
@@ -94,6 +94,27 @@ def test_transformer_forward_matches_reference_golden(name):
     # `ref` and `got`, so both are compared against the fixture itself
     three_way(got, ref, t["out"], name=name + "_vs_reference_fixture")
     three_way(got, ref, truth32, name=name)
+
+
+def test_control_ref_and_clip_tokens_match_reference_golden():
+    """v5.1 Control with a reference image (+ CLIP tokens): ref_proj patch tokens + resized 2-D sin-cos table in place of the
+    text tokens (transformer3d.py:1420-1429,1538-1561), against outputs of the REFERENCE module (fixture minted by
+    tests/golden/make_golden.py) and the oracle."""
+    from oracle import dit
+    t, cfg, (B, F, H, W, St), (o32, ob, ours) = prelude_reference_golden("dit_ref_control_ref_clip")
+    rope = dit.rope_for_video(H * 8, W * 8, F)
+    tb = t["timestep"].to(bf16)
+    lat, enc, refl, clip = (t[k].to(bf16) for k in ("latents", "encoder_hidden_states", "ref_latents", "clip_encoder_hidden_states"))
+    for key, clip_in in (("out", clip), ("out_ref_only", None)):
+        with torch.no_grad():
+            truth32 = o32(lat.float(), tb.float(), encoder_hidden_states=enc.float(), image_rotary_emb=rope, ref_latents=refl.float(),
+                          clip_encoder_hidden_states=None if clip_in is None else clip_in.float())[0]
+            ref = ob(lat, tb, encoder_hidden_states=enc, image_rotary_emb=rope, ref_latents=refl, clip_encoder_hidden_states=clip_in)[0]
+            got = ours(lat.cuda(), tb.cuda(), encoder_hidden_states=enc.cuda(), image_rotary_emb=(rope[0].cuda(), rope[1].cuda()),
+                       ref_latents=refl.cuda(), clip_encoder_hidden_states=None if clip_in is None else clip_in.cuda(),
+                       return_dict=False)[0]
+        three_way(got, ref, t[key], name=f"control_ref_clip[{key}]_vs_reference_fixture")
+        three_way(got, ref, truth32, name=f"control_ref_clip[{key}]")
 
 
 def test_transformer_forward_is_deterministic():

@@ -37,7 +37,7 @@ def test_prelude_dit_build(cfg_name):
     assert set(ours.state_dict()) == set(ob.state_dict())
 
 
-@pytest.mark.parametrize("name", ["dit_ref_t2v", "dit_ref_i2v_inpaint", "dit_ref_3heads_3layers"])
+@pytest.mark.parametrize("name", ["dit_ref_t2v", "dit_ref_i2v_inpaint", "dit_ref_3heads_3layers", "dit_ref_control_ref_clip"])
 def test_prelude_dit_reference_golden(name):
     from tests import test_dit_module_gpu as T
     t, cfg, shape, (o32, ob, ours) = T.prelude_reference_golden(name, device="cpu")

@@ -222,3 +222,28 @@ def test_control_latents_channel_concat_host_logic(monkeypatch):
         got = ours(lat, t, encoder_hidden_states=enc, image_rotary_emb=rope, inpaint_latents=inp, control_latents=ctl,
                    return_dict=False)[0]
     assert _rel(got, ref) < 2e-2
+
+
+@pytest.mark.parametrize("with_clip", [False, True])
+def test_control_ref_and_clip_tokens_host_logic(monkeypatch, with_clip):
+    """v5.1 Control with a reference image (transformer3d.py:1420-1429,1538-1561): ref_proj patch tokens + the resized 2-D
+    sin-cos table REPLACE the text tokens; CLIP tokens (clip_proj) are concatenated in front of them."""
+    cpu_ops.install(monkeypatch)
+    cfg = dict(CFG, ref_channels=16, clip_channels=96, sample_width=20, sample_height=12)
+    ob, ours = _models(cfg)
+    assert ours.ref_pos_embedding.dtype == bf16 and torch.equal(ours.ref_pos_embedding, ob.ref_pos_embedding)
+    g = torch.Generator().manual_seed(4)
+    lat = torch.randn(2, 16, 2, 8, 12, generator=g).to(bf16)
+    enc = (torch.randn(2, 9, 128, generator=g) * 3).to(bf16)
+    refl = torch.randn(2, 16, 1, 8, 12, generator=g).to(bf16)
+    clip = torch.randn(2, 5, 96, generator=g).to(bf16) if with_clip else None
+    t = torch.tensor([500.0, 300.0]).to(bf16)
+    rope = dit.rope_for_video(64, 96, 2)
+    with torch.no_grad():
+        ref = ob(lat, t, encoder_hidden_states=enc, image_rotary_emb=rope, ref_latents=refl, clip_encoder_hidden_states=clip)[0]
+        got = ours(lat, t, encoder_hidden_states=enc, image_rotary_emb=rope, ref_latents=refl, clip_encoder_hidden_states=clip,
+                   return_dict=False)[0]
+        plain = ours(lat, t, encoder_hidden_states=enc, image_rotary_emb=rope, return_dict=False)[0]
+    assert _rel(got, ref) < 2e-2 and _rel(got, plain) > 2 * _rel(got, ref)  # (the reference-image tokens do change the result)
+    with pytest.raises(ValueError):
+        ours(lat, t, encoder_hidden_states=enc, image_rotary_emb=rope, clip_encoder_hidden_states=torch.zeros(2, 5, 96).to(bf16))

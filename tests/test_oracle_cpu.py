@@ -128,6 +128,21 @@ def test_dit_oracle_matches_reference_golden(name):
     torch.testing.assert_close(out, t["out"], rtol=1e-5, atol=1e-6)
 
 
+def test_dit_oracle_control_ref_clip_matches_reference_golden():
+    """The Control model's reference-image / CLIP token branches (transformer3d.py:1420-1429,1538-1561), fixture minted by
+    the reference module; the 2-D sin-cos table is diffusers' (restated, unpinned) in oracle and shim alike."""
+    t, meta, cfg, m = _dit_case("dit_ref_control_ref_clip")
+    m = m.to(torch.float32)  # the float64 position-table buffer follows the module dtype, like under .to(bfloat16)
+    rope = dit.rope_for_video(64, 96, 2)
+    kw = dict(encoder_hidden_states=t["encoder_hidden_states"], image_rotary_emb=rope, ref_latents=t["ref_latents"])
+    with torch.no_grad():
+        out = m(t["latents"], t["timestep"], clip_encoder_hidden_states=t["clip_encoder_hidden_states"], **kw)[0]
+        out_ref_only = m(t["latents"], t["timestep"], **kw)[0]
+    torch.testing.assert_close(out, t["out"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(out_ref_only, t["out_ref_only"], rtol=1e-5, atol=1e-6)
+    assert not torch.allclose(out, out_ref_only, atol=1e-3)
+
+
 def test_dit_oracle_teacache_matches_reference_golden():
     """Six calls of the reference model with TeaCache enabled: same skip decisions, same outputs."""
     t, meta, cfg, m = _dit_case("dit_ref_teacache")

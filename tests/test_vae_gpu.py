@@ -81,9 +81,9 @@ def test_conv3d_output_row_window_is_the_same_convolution(T, H, W, Cin, Cout, va
 
 
 def test_groupnorm_from_gathered_sums_and_attention_query_rows():
-    """The strip-parallel forms of GroupNorm and of the mid-block attention: one part == ea_groupnorm_stats bit for bit, two
-    parts (rows split 9 + 12) the same up to the association of two fp64 additions; query rows [p0, p1) of the attention are
-    the same rows of the full evaluation."""
+    """The strip-parallel forms of GroupNorm and of the mid-block attention: one part == ea_groupnorm_stats bit for bit, and so
+    are two parts (rows split 9 + 12): the statistics are accumulated per image row and the rows added in fp64 (exact
+    additions), so the split does not matter; query rows [p0, p1) of the attention are the same rows of the full evaluation."""
     from easyanimate_b200 import vae_ops
     T, H, W, Cc, G = 3, 21, 16, 128, 32
     x = _rand((T, H, W, Cc), 2.0, 1) + 0.5
@@ -96,8 +96,7 @@ def test_groupnorm_from_gathered_sums_and_attention_query_rows():
     sums = torch.stack([vae_ops.groupnorm_sums(a, G), vae_ops.groupnorm_sums(b, G)]).contiguous()
     two = torch.cat([vae_ops.groupnorm_from_sums(a, sums, count, gamma, beta, G, 1e-6, True),
                      vae_ops.groupnorm_from_sums(b, sums, count, gamma, beta, G, 1e-6, True)], dim=1)
-    assert (two.float() - ref.float()).abs().max().item() <= 2 ** -7 * ref.float().abs().max().item()
-    assert (two != ref).float().mean().item() < 1e-3
+    assert torch.equal(two, ref)
     # attention query rows
     C2 = 128
     n, res = _rand((T * H * W, C2), 1.0, 4), _rand((T * H * W, C2), 1.0, 5)
