@@ -66,7 +66,7 @@ struct Cfg {
   static constexpr uint32_t kColO = kColP + NT * (KT / 2);
   static_assert(kColO + NT * kHD <= 512, "TMEM budget");
   // registers: the producer/MMA warpgroup shrinks to 40, the softmax warpgroups grow to kSoftmaxRegs
-  static constexpr int kSoftmaxRegs = NT == 2 ? 232 : 152;
+  static constexpr int kSoftmaxRegs = NT == 2 ? 232 : (NT == 3 ? 152 : 96);
 };
 
 EA_DEVICE void tmem_st16(uint32_t taddr, const uint32_t* r) {
@@ -343,7 +343,9 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
   } else {
     // ---- softmax warpgroups: take them
     if constexpr (NT == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    else asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    else if constexpr (NT == 3) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    // (NT == 4: the kernel is compiled for 96 registers - 65 536 / 640 threads - and the 128 x 56 the other warpgroup releases
+    //  would not cover an increase of all 512 softmax threads past 104: setmaxnreg.inc only draws from the CTA's own pool)
     // ===== softmax / correction / epilogue: tile t, one query row per thread =====
     const int t = warp >> 2;
     const int ew = warp & 3;
@@ -413,8 +415,19 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
           tmem_st16(tP + 32, pk);
           exp_pairs<POLY, 0, 16, TRUNC, PDEN>(s + 96, c2, nm2, acc2, guard, pk2);
           tmem_st16(tP + 48, pk2);
+        } else if constexpr (KT == 32) {
+          // one 32-column chunk per block: four softmax warps per SM sub-partition, a quarter of the work per block
+          tmem_ld32p(tS, s);
+          tmem_ld_fence(s);
+          tc_fence_before();
+          bar_arrive(bar_t + kSFree);  // S_t may be overwritten by QK_{j+1}
+          exp_pairs<POLY, 0, 8, TRUNC, PDEN>(s, c2, nm2, acc2, guard, pk);
+          bar_wait(bar_t + kODone, (j - 1) & 1);  // PV_{j-1} has read P_t
+          tc_fence_after();
+          exp_pairs<POLY, 8, 16, TRUNC, PDEN>(s, c2, nm2, acc2, guard, pk);
+          tmem_st16(tP, pk);
         } else {
-          static_assert(KT == 64 || KT == 128, "key block of 64 or 128");
+          static_assert(KT == 64 || KT == 128, "key block of 32, 64 or 128");
           tmem_ld32p(tS, s);
           tmem_ld_fence(s);
           tmem_ld32p(tS + 32, s + 32);
@@ -601,6 +614,10 @@ static int launch(const ea_attn_args* g, cudaStream_t stream) {
 
 int launch_attn6(const ea_attn_args* g, int poly, cudaStream_t stream) {
   const bool trunc = (g->variant & 0x800) != 0;  // experimental: P by truncation (PRMT) instead of F2FP round-to-nearest
+  if (g->variant & 0x4000) {  // four query tiles per CTA, 32-key blocks (experimental)
+    if (poly != 0) return fail(EA_ERR_INVALID, "ea_attn_fwd: the 4 x 32 layout takes no polynomial pairs");
+    return trunc ? a6::launch<0, false, true, 4, 32>(g, stream) : a6::launch<0, false, false, 4, 32>(g, stream);
+  }
   if (g->variant & 0x2000) {  // three query tiles per CTA, 64-key blocks
     switch (poly) {
       case 0: return trunc ? a6::launch<0, false, true, 3, 64>(g, stream) : a6::launch<0, false, false, 3, 64>(g, stream);

@@ -40,7 +40,7 @@ def bench_gemm():
 
 def bench_attn():
     from easyanimate_b200 import ops
-    variant = int(os.environ.get("EA_ATTN_VARIANT", "0x210c"), 0)
+    variant = int(os.environ.get("EA_ATTN_VARIANT", "0x217c"), 0)
     compare = not os.environ.get("EA_ATTN_NO_COMPARE")
     shapes = [(1, 48, 13312 + 256, 256), (1, 48, 47056, 256)]
     if os.environ.get("EA_ATTN_SMALL"):
