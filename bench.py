@@ -76,7 +76,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -523,12 +523,14 @@ def main():
             inpaint = torch.randn((1, 17, F, h, w), device=dev, generator=g).to(bf16)
         return model, sampler, rope, latents, embeds, inpaint
 
-    def timed_steps(sampler, latents, embeds, rope, inpaint, steps, warmup, collect_attn=False):
+    def timed_steps(sampler, latents, embeds, rope, inpaint, steps, warmup, collect_attn=False, clocks=None):
         sampler.set_timesteps(max(2 * (warmup + steps) + 8, 30), device="cpu")
         latents, i = run_steps(sampler, latents, embeds, rope, warmup, 0, inpaint)
         events = [] if collect_attn else None
         ops.ATTN_TIMING = events
         sync_all()
+        if clocks is not None:
+            clocks.start()  # sampled DURING the timed region only (warm-up and buffer set-up are over)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _lib.ea_launch_count()
         e0.record()
@@ -548,8 +550,8 @@ def main():
     model, sampler, rope, latents, embeds, inpaint = setup(preset)
     n_params = sum(p.numel() for p in model.parameters())
     clocks = ClockSampler(local_rank)
-    clocks.start()
-    ms_total, launches, attn_ms, latents, step_i = timed_steps(sampler, latents, embeds, rope, inpaint, args.steps, args.warmup, True)
+    ms_total, launches, attn_ms, latents, step_i = timed_steps(sampler, latents, embeds, rope, inpaint, args.steps, args.warmup, True,
+                                                               clocks=clocks)
     clock_info = clocks.stop()
 
     # ---- end to end through the public API with HOST buffers (H2D inputs + D2H result every step)

@@ -135,6 +135,7 @@ ea_cfg_euler_step = _sig("ea_cfg_euler_step", [vp, vp, vp, vp, i64, f32, i32, f3
 ea_l1_sums = _sig("ea_l1_sums", [vp, vp, vp, i64, vp])
 ea_ew_addsub = _sig("ea_ew_addsub", [vp, vp, vp, i64, i32, vp])
 ea_dequant_e4m3 = _sig("ea_dequant_e4m3", [vp, vp, i64, vp])
+ea_ipc_export = _sig("ea_ipc_export", [vp, vp, C.POINTER(i64)])
 ea_ipc_open = _sig("ea_ipc_open", [vp, C.POINTER(vp)])
 ea_ipc_close = _sig("ea_ipc_close", [vp])
 ea_conv3d_causal = _sig("ea_conv3d_causal", [C.POINTER(ConvArgs), vp])

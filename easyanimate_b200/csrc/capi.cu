@@ -4,6 +4,8 @@
 
 #include <string>
 
+#include <cuda.h>
+
 #include "host.h"
 #include "../../include/ea_b200.h"
 
@@ -38,6 +40,37 @@ extern "C" int ea_enable_peer_access(int32_t peer_device) {
 // (cudaIpcMemLazyEnablePeerAccess then sets up peer access from it to the exporting device): a mapping opened under the
 // exporter's device index - what torch's own storage sharing does - is readable by copy engines but faults when a kernel
 // of another device dereferences it (profiles/r02_debug_sp_ipc.log).
+// Export side: the 64-byte handle of the device allocation that contains `ptr` (cuMemGetAddressRange finds its base; torch's
+// caching allocator sub-allocates from cudaMalloc'ed segments) and ptr's byte offset inside it.
+extern "C" int ea_ipc_export(const void* ptr, void* handle64_out, int64_t* offset_out) {
+  if (!ptr || !handle64_out || !offset_out) return ea::fail(EA_ERR_INVALID, "ea_ipc_export: null pointer");
+  typedef CUresult (*GetRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+  static GetRangeFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !f) {
+      (void)cudaGetLastError();
+      return ea::fail(EA_ERR_CUDA, "ea_ipc_export: cuMemGetAddressRange unavailable");
+    }
+    fn = reinterpret_cast<GetRangeFn>(f);
+  }
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  CUresult r = fn(&base, &size, reinterpret_cast<CUdeviceptr>(ptr));
+  if (r != CUDA_SUCCESS) return ea::fail(EA_ERR_CUDA, "ea_ipc_export: cuMemGetAddressRange failed with CUresult " + std::to_string((int)r));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base));
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return ea::fail(EA_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e) +
+                                     " (the buffer must come from a cudaMalloc'ed segment: no expandable_segments / cudaMallocAsync)");
+  }
+  memcpy(handle64_out, &h, sizeof(h));
+  *offset_out = (int64_t)(reinterpret_cast<CUdeviceptr>(ptr) - base);
+  return EA_OK;
+}
+
 extern "C" int ea_ipc_open(const void* handle64, void** base_out) {
   if (!handle64 || !base_out) return ea::fail(EA_ERR_INVALID, "ea_ipc_open: null pointer");
   cudaIpcMemHandle_t h;

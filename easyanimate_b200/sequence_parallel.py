@@ -49,17 +49,6 @@ def all_reduce_floats(values, group) -> list:
 _IPC_OPEN = {}  # handle bytes -> [mapped base address, users]
 
 
-def _raw_ipc_handle(h: bytes) -> bytes:
-    """torch's shareable handle string -> the 64-byte cudaIpcMemHandle_t.  Recent torch prefixes two bytes (a version and the
-    kind: 'c' = a cudaMalloc'ed segment, 'e' = an expandable segment, which has no cudaIpcMemHandle_t)."""
-    if len(h) == 64:
-        return h
-    if len(h) == 66 and h[1:2] == b"c":
-        return h[2:]
-    raise ValueError(f"unsupported CUDA IPC handle from torch ({len(h)} bytes, kind {h[1:2]!r}): the peer-store exchange needs "
-                     "cudaMalloc'ed segments (do not enable expandable_segments), or run EA_SP_MODE=nccl")
-
-
 def _ipc_open(handle: bytes) -> int:
     from . import _lib as L
     ent = _IPC_OPEN.get(handle)
@@ -113,11 +102,13 @@ class PeerExchange:
         self.out_video = part(3, (B, S_loc, H * 64))
         self.out_text = part(4, (B, S_t, H * 64))
         self._flag = torch.zeros((1,), device=device, dtype=torch.int32)
-        # export: the allocation's cudaIpcMemHandle_t and this buffer's byte offset inside it (torch's storage sharing looks both
-        # up in its caching allocator).  The peers do NOT import through torch - it would open the mapping under the exporter's
-        # device index, which a kernel of another device cannot dereference - but through ea_ipc_open on their own device.
-        share = self._buf.untyped_storage()._share_cuda_()
-        handle, base_off = _raw_ipc_handle(bytes(share[1])), int(share[3]) + self._buf.storage_offset()
+        # export: the cudaIpcMemHandle_t of the device allocation that holds the buffer and the buffer's byte offset inside it
+        # (torch's caching allocator sub-allocates from cudaMalloc'ed segments).  The peers import it with ea_ipc_open on THEIR
+        # device: a mapping opened under the exporter's device index - what torch's own storage sharing does - cannot be
+        # dereferenced by a kernel of another device.
+        hbuf, hoff = (C.c_char * 64)(), L.i64(0)
+        L.check(L.ea_ipc_export(self._buf.data_ptr(), hbuf, C.byref(hoff)), "ea_ipc_export")
+        handle, base_off = bytes(hbuf.raw), int(hoff.value)
         gathered = [None] * P
         dist.all_gather_object(gathered, (torch.cuda.current_device(), handle, base_off), group=group)
         self._opened = []  # mapped bases, closed by release()

@@ -238,9 +238,12 @@ int ea_attn_generations(void);
  * device may then dereference pointers into `peer_device`'s memory (ea_qkv_peers / ea_attn_peers buffers). */
 int ea_enable_peer_access(int32_t peer_device);
 
+/* Export a device buffer to the other processes of the node (the 64-byte cudaIpcMemHandle_t of the allocation that holds
+ * `ptr`, and ptr's byte offset in it), and import one: */
 /* Import a peer process's device allocation (a 64-byte cudaIpcMemHandle_t of its base) into the CURRENT device's context so
  * that kernels launched on the current device may store into it (cudaIpcOpenMemHandle with lazy peer access); base_out is
  * the mapped base address.  One open per handle and process; ea_ipc_close unmaps. */
+int ea_ipc_export(const void* ptr, void* handle64_out, int64_t* offset_out); /* handle of the allocation holding ptr + ptr's offset */
 int ea_ipc_open(const void* handle64, void** base_out);
 int ea_ipc_close(void* base);
 

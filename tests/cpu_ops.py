@@ -214,7 +214,8 @@ def groupnorm_from_sums(x, sums_all, count, gamma, beta, groups, eps, silu):
     cpg = C // groups
     m = mean.repeat_interleave(cpg, dim=1)[:, None, None, :]
     r_ = rstd.repeat_interleave(cpg, dim=1)[:, None, None, :]
-    y = _r((x.float() - m) * r_ * gamma.float() + beta.float())
+    a = r_ * gamma.float()  # the affine form of PyTorch's GroupNorm kernels and of gn_apply2_kernel: y = a x + b
+    y = _r(x.float() * a + (beta.float() - a * m))
     if silu:
         y = _r(torch.nn.functional.silu(y))
     return y.contiguous().to(bf16)
