@@ -96,3 +96,21 @@ def test_cfg_euler_step():
     out1 = ops.cfg_euler_step(pred[:1], lat, 1.0, sig.item(), sig_next.item(), use_cfg=False)
     ref1 = (lat.float() + (sig_next - sig).cuda() * pred[:1]).to(bf16)
     assert torch.equal(out1, ref1)
+
+
+def test_ipc_export_names_the_allocation_that_holds_a_buffer():
+    """ea_ipc_export (sequence-parallel peer buffers): a sub-allocation of torch's caching allocator is exported as the
+    cudaIpcMemHandle_t of its cudaMalloc'ed segment + its byte offset; two buffers carved from one segment share the handle."""
+    import ctypes as C
+    from easyanimate_b200 import _lib as L
+    a = torch.empty(1 << 16, device="cuda", dtype=torch.uint8)   # both come from the same 2 MB small-block segment
+    b = torch.empty(1 << 16, device="cuda", dtype=torch.uint8)
+    out = []
+    for t in (a, b):
+        h, off = (C.c_char * 64)(), L.i64(0)
+        L.check(L.ea_ipc_export(t.data_ptr(), h, C.byref(off)), "ea_ipc_export")
+        out.append((bytes(h.raw), off.value))
+        assert off.value >= 0 and any(h.raw)
+    if out[0][0] == out[1][0]:  # same segment: the offsets differ by the distance of the buffers
+        assert out[1][1] - out[0][1] == b.data_ptr() - a.data_ptr()
+    assert L.ea_ipc_export(None, (C.c_char * 64)(), C.byref(L.i64(0))) != 0
