@@ -12,3 +12,5 @@ __version__ = "0.31.0"
 class AutoencoderKL:  # imported by easyanimate/models/autoencoder_magvit.py:41, never used on the decode path
     def __init__(self, *a, **k):
         raise NotImplementedError("diffusers shim: AutoencoderKL is a placeholder")
+
+from .pipelines.pipeline_utils import DiffusionPipeline  # noqa: E402  (pipeline_easyanimate.py:22)

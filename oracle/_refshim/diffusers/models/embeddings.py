@@ -100,3 +100,16 @@ def get_2d_sincos_pos_embed(embed_dim, grid_size, cls_token=False, extra_tokens=
 
 def get_3d_sincos_pos_embed(*a, **k):
     raise NotImplementedError("diffusers shim: get_3d_sincos_pos_embed is not on the EasyAnimateV5.1 path")
+
+
+def get_3d_rotary_pos_embed(embed_dim, crops_coords, grid_size, temporal_size, theta=10000, use_real=True):
+    """diffusers 0.30/0.31 embeddings.get_3d_rotary_pos_embed (called at pipeline_easyanimate.py:1006-1009): ONE restatement,
+    kept in oracle/dit.py (third-party, unpinned - tests/test_diffusers_pin.py compares it with a real diffusers if present)."""
+    from oracle.dit import get_3d_rotary_pos_embed as _impl
+
+    assert use_real
+    return _impl(embed_dim, crops_coords, grid_size, temporal_size, theta)
+
+
+def get_2d_rotary_pos_embed(*a, **k):
+    raise NotImplementedError("diffusers shim: get_2d_rotary_pos_embed is not on the EasyAnimateV5.1 path (3d_rope)")

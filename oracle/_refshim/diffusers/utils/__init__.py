@@ -29,3 +29,30 @@ class _Logging:
 
 
 logging = _Logging()
+
+
+# ---- names the reference PIPELINE files import (pipeline_easyanimate.py:33-36)
+BACKENDS_MAPPING = {}
+
+
+def deprecate(*args, **kwargs):
+    pass
+
+
+def is_bs4_available() -> bool:
+    return False
+
+
+def is_ftfy_available() -> bool:
+    return False
+
+
+def is_torch_xla_available() -> bool:
+    return False
+
+
+def replace_example_docstring(example_docstring):
+    def wrap(fn):
+        return fn
+
+    return wrap

@@ -188,6 +188,59 @@ def make_dit_reference():
     print("dit_ref_teacache skipped:", skipped)
 
 
+PIPE_CFG = dict(num_attention_heads=4, attention_head_dim=64, in_channels=16, out_channels=16, patch_size=2, num_layers=2,
+                time_embed_dim=128, add_norm_text_encoder=True, text_embed_dim=256, text_embed_dim_t5=None)
+PIPE_BOC = (64, 64, 128, 128)
+
+
+def pipeline_case_modules(dtype, transformer_seed=41, vae_seed=42):
+    """bf16-rounded weights in `dtype` for the reference-pipeline fixture: (oracle transformer, oracle VAE) state dicts are
+    what both the reference modules here and the product modules in tests/test_pipeline_gpu.py load."""
+    ot = dit.init_weights_(dit.OracleTransformer3D(**PIPE_CFG), transformer_seed)
+    ov = vae.init_weights_(vae.OracleAutoencoderKLMagvit(block_out_channels=list(PIPE_BOC)), vae_seed)
+    for m in (ot, ov):
+        m.load_state_dict({k: v.to(torch.bfloat16).to(dtype) for k, v in m.state_dict().items()})
+    return ot.to(dtype), ov.to(dtype)
+
+
+def pipeline_case_inputs(seed=43):
+    g = torch.Generator().manual_seed(seed)
+    lat = torch.randn(1, 16, 3, 8, 12, generator=g).to(torch.bfloat16)
+    pe = (torch.randn(1, 24, PIPE_CFG["text_embed_dim"], generator=g) * 3).to(torch.bfloat16)
+    ne = (torch.randn(1, 24, PIPE_CFG["text_embed_dim"], generator=g) * 3).to(torch.bfloat16)
+    return lat, pe, ne
+
+
+def make_pipeline_reference():
+    """`pipe_ref_t2v.safetensors`: the REFERENCE's own EasyAnimatePipeline.__call__ (pipeline_easyanimate.py:764-1160, through
+    oracle/ref_pipeline.py) over the reference's own transformer and VAE: 4 CFG flow-matching steps + decode_latents, once in
+    bf16 (the execution the product reproduces) and once in fp32 with the same bf16-rounded weights (the truth of the
+    three-way criterion).  Stored: the inputs, the final latents of both runs, the frames of both runs."""
+    from oracle import ref_pipeline
+    lat, pe, ne = pipeline_case_inputs()
+    t = {"latents": lat, "prompt_embeds": pe, "negative_prompt_embeds": ne}
+    for tag, dtype in (("bf16", torch.bfloat16), ("fp32", torch.float32)):
+        ot, ov = pipeline_case_modules(dtype)
+        rt = ref_dit.reference_transformer(**PIPE_CFG, time_position_encoding_type="3d_rope").eval().to(dtype)
+        rt.load_state_dict(ot.state_dict(), strict=True)
+        rv = ref_vae.reference_autoencoder(block_out_channels=PIPE_BOC).eval().to(dtype)
+        missing, unexpected = rv.load_state_dict(ov.state_dict(), strict=False)
+        assert not unexpected and all(k.startswith(("encoder.", "quant_conv")) for k in missing)
+        pipe = ref_pipeline.reference_pipeline(rt, rv)
+        seen, orig = {}, pipe.decode_latents
+        pipe.decode_latents = lambda z, seen=seen, orig=orig: (seen.setdefault("z", z.clone()), orig(z))[1]
+        frames = ref_pipeline.run(pipe, lat.to(dtype), pe.to(dtype), ne.to(dtype), height=64, width=96, video_length=9,
+                                  num_inference_steps=4, guidance_scale=6.0)
+        t[f"z_{tag}"], t[f"frames_{tag}"] = seen["z"].contiguous(), frames.contiguous()
+        print("pipe_ref_t2v", tag, tuple(frames.shape), float(frames.mean()), float(seen["z"].float().std()))
+    save_file(t, os.path.join(HERE, "pipe_ref_t2v.safetensors"),
+              metadata={"source": "reference EasyAnimatePipeline.__call__ + reference transformer + reference AutoencoderKLMagvit "
+                                  "(CPU; diffusers names from oracle/_refshim: FlowMatchEulerDiscreteScheduler shift=1, "
+                                  "get_3d_rotary_pos_embed)", "config": repr(PIPE_CFG), "block_out_channels": repr(PIPE_BOC),
+                        "steps": "4", "guidance_scale": "6.0", "height": "64", "width": "96", "video_length": "9",
+                        "seeds": "transformer 41, vae 42, inputs 43"})
+
+
 TEACACHE_COEFFS = [1.07862322, -4.19362456, 3.06725828, 0.33161686, 0.02374758]  # transformer3d.py:131 (v5.1-7b)
 
 
@@ -199,3 +252,4 @@ if __name__ == "__main__":
     make_vae_encode()
     make_dit()
     make_dit_reference()
+    make_pipeline_reference()

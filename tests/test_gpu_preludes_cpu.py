@@ -49,6 +49,7 @@ def test_prelude_sampler_and_pipeline_tests():
     T.prelude_sampler(device="cpu")
     T.prelude_decode_latents(device="cpu")
     T.prelude_from_pretrained_2d(device="cpu")
+    T.prelude_reference_pipeline_golden(device="cpu")
 
 
 def test_gpu_test_modules_import_without_a_gpu():

@@ -143,6 +143,53 @@ def test_frames_out_kernel_bit_exact_including_ragged_tail_and_nan():
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# a1 + a10 against the REFERENCE's own pipeline call (fixture minted by EasyAnimatePipeline.__call__ itself)
+# ---------------------------------------------------------------------------------------------------------------
+def prelude_reference_pipeline_golden(device="cuda"):
+    """tests/golden/pipe_ref_t2v.safetensors (make_golden.make_pipeline_reference): inputs, final latents and frames of the
+    reference's EasyAnimatePipeline.__call__ over the reference's transformer + VAE, in bf16 and in fp32.  The product modules
+    load the same seeded, bf16-rounded weights."""
+    from safetensors import safe_open
+    from easyanimate_b200.autoencoder_magvit import AutoencoderKLMagvit
+    from easyanimate_b200.pipeline import EasyAnimateSampler
+    from easyanimate_b200.transformer3d import EasyAnimateTransformer3DModel
+    from tests.golden import make_golden as G
+    path = os.path.join(os.path.dirname(__file__), "golden", "pipe_ref_t2v.safetensors")
+    with safe_open(path, "pt") as f:
+        t = {k: f.get_tensor(k) for k in f.keys()}
+        meta = f.metadata()
+    ot, ov = G.pipeline_case_modules(bf16)
+    lat, pe, ne = G.pipeline_case_inputs()
+    assert torch.equal(lat, t["latents"]) and torch.equal(pe, t["prompt_embeds"]) and torch.equal(ne, t["negative_prompt_embeds"])
+    ours_t = EasyAnimateTransformer3DModel(**G.PIPE_CFG).to(bf16)
+    ours_t.load_state_dict(ot.state_dict(), strict=True)
+    ours_v = AutoencoderKLMagvit(latent_channels=16, cache_mag_vae=True, spatial_group_norm=True, mid_block_attention_type="spatial",
+                                 block_out_channels=list(G.PIPE_BOC), scaling_factor=0.7125).to(bf16)
+    missing, unexpected = ours_v.load_state_dict(ov.state_dict(), strict=False)
+    assert not unexpected and all(k.startswith(("quant_conv", "encoder.")) for k in missing)
+    sampler = EasyAnimateSampler(ours_t.to(device), vae=ours_v.to(device), guidance_scale=float(meta["guidance_scale"]))
+    return t, meta, sampler
+
+
+@gpu
+def test_sampler_and_decode_match_the_reference_pipeline_call():
+    """The whole hot path - 4 CFG flow-matching steps, decode_latents, float32 frames on the host - against what the reference's
+    own `EasyAnimatePipeline.__call__` produced from the same latents / embeddings / weights (bf16 run = reference execution,
+    fp32 run = truth)."""
+    t, meta, sampler = prelude_reference_pipeline_golden()
+    h, w, steps = int(meta["height"]), int(meta["width"]), int(meta["steps"])
+    z = sampler.sample(t["latents"].cuda(), t["prompt_embeds"].cuda(), t["negative_prompt_embeds"].cuda(), height=h, width=w,
+                       num_inference_steps=steps)
+    three_way(z, t["z_bf16"], t["z_fp32"], slack=2.0, name="reference_pipeline_latents")
+    frames = sampler.decode_latents(z)
+    assert frames.shape == t["frames_fp32"].shape == (1, 3, int(meta["video_length"]), h, w) and frames.dtype == torch.float32
+    three_way(frames, t["frames_bf16"], t["frames_fp32"], slack=2.0, name="reference_pipeline_frames")
+    # the decode on its own, from the reference's latents: isolates the VAE from the loop's compounding
+    frames_ref_z = sampler.decode_latents(t["z_bf16"].cuda())
+    three_way(frames_ref_z, t["frames_bf16"], t["frames_fp32"], name="reference_pipeline_decode_of_reference_latents")
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # a17 / boundary: checkpoint loaders
 # ---------------------------------------------------------------------------------------------------------------
 def _write_transformer_dir(path, cfg, state):

@@ -1,0 +1,105 @@
+"""SURVEY.md section 8b, the boundary's strongest proof available without a GPU: the REFERENCE's own
+`EasyAnimatePipeline.__call__` (easyanimate/pipeline/pipeline_easyanimate.py:764-1160, executed unmodified from
+/root/reference through oracle/ref_pipeline.py) driving
+
+  (1) the reference's own transformer + VAE  -> pins oracle.dit.denoise_loop + oracle.vae decode + the decode_latents tail
+      (what every GPU parity test compares with) against the reference's loop, not against a restatement of it;
+  (2) the PRODUCT modules (easyanimate_b200.EasyAnimateTransformer3DModel / AutoencoderKLMagvit, kernels replaced by the
+      torch stand-ins of tests/cpu_ops.py) plugged into the same unmodified pipeline object -> every attribute, keyword and
+      return convention the reference pipeline touches exists on the product modules and means the same thing.
+
+Skipped where /root/reference is absent (the GPU box); the GPU-side counterpart is the fixture `pipe_ref_t2v.safetensors`
+minted by (1) (tests/golden/make_golden.py) and compared with in tests/test_pipeline_gpu.py."""
+import pytest
+import torch
+
+from oracle import dit, ref_pipeline, vae
+from tests import cpu_ops
+
+pytestmark = pytest.mark.skipif(not ref_pipeline.available(), reason="/root/reference not present")
+bf16 = torch.bfloat16
+CFG = dict(num_attention_heads=2, attention_head_dim=64, in_channels=16, out_channels=16, patch_size=2, num_layers=2,
+           time_embed_dim=64, add_norm_text_encoder=True, text_embed_dim=128, text_embed_dim_t5=None)
+BOC = (64, 64, 128, 128)
+H, W, FRAMES, LF, STEPS = 64, 96, 5, 2, 3
+
+
+def _inputs(seed=5):
+    g = torch.Generator().manual_seed(seed)
+    lat = torch.randn(1, 16, LF, H // 8, W // 8, generator=g)
+    pe, ne = torch.randn(1, 9, 128, generator=g) * 3, torch.randn(1, 9, 128, generator=g) * 3
+    return lat, pe, ne
+
+
+def _reference_modules(dtype):
+    from oracle import ref_dit, ref_vae
+    rt = ref_dit.reference_transformer(**CFG, time_position_encoding_type="3d_rope").eval()
+    rt.load_state_dict(dit.init_weights_(dit.OracleTransformer3D(**CFG), 31).state_dict(), strict=True)
+    rv = ref_vae.reference_autoencoder(block_out_channels=BOC).eval()
+    rv.load_state_dict(vae.init_weights_(vae.OracleAutoencoderKLMagvit(block_out_channels=list(BOC)), 32).state_dict(), strict=False)
+    return rt.to(dtype), rv.to(dtype)
+
+
+def _oracle_frames(lat, pe, ne, dtype):
+    ot = dit.init_weights_(dit.OracleTransformer3D(**CFG), 31).to(dtype)
+    ov = vae.init_weights_(vae.OracleAutoencoderKLMagvit(block_out_channels=list(BOC)), 32).to(dtype)
+    with torch.no_grad():
+        z = dit.denoise_loop(ot, lat.to(dtype), pe.to(dtype), ne.to(dtype), dit.rope_for_video(H, W, LF), num_steps=STEPS,
+                             guidance_scale=6.0)
+        video = ov.decode(1 / ov.scaling_factor * z)[0].clamp(-1, 1)
+        return z, (video / 2 + 0.5).clamp(0, 1).float()
+
+
+def test_reference_pipeline_call_pins_the_oracle_loop_fp32():
+    lat, pe, ne = _inputs()
+    rt, rv = _reference_modules(torch.float32)
+    pipe = ref_pipeline.reference_pipeline(rt, rv)
+    frames = ref_pipeline.run(pipe, lat, pe, ne, height=H, width=W, video_length=FRAMES, num_inference_steps=STEPS)
+    _, want = _oracle_frames(lat, pe, ne, torch.float32)
+    assert frames.shape == want.shape == (1, 3, FRAMES, H, W) and frames.dtype == torch.float32
+    assert (frames - want).abs().max().item() < 2e-5  # two fp32 evaluations of the same graph
+
+
+def test_reference_pipeline_call_pins_the_oracle_loop_bf16():
+    """In bf16 the loop's rounding points matter (timestep to bf16, CFG combine in bf16, (sigma_next - sigma) rounded to bf16
+    by type promotion, fp32 sample): the oracle's loop reproduces the reference pipeline's latents bit for bit."""
+    lat, pe, ne = _inputs(6)
+    rt, rv = _reference_modules(bf16)
+    pipe = ref_pipeline.reference_pipeline(rt, rv)
+    seen = {}
+    orig = pipe.decode_latents
+    pipe.decode_latents = lambda z: (seen.setdefault("z", z.clone()), orig(z))[1]
+    frames = ref_pipeline.run(pipe, lat.to(bf16), pe.to(bf16), ne.to(bf16), height=H, width=W, video_length=FRAMES,
+                              num_inference_steps=STEPS)
+    z, want = _oracle_frames(lat, pe, ne, bf16)
+    assert torch.equal(seen["z"], z)
+    assert (frames - want).abs().max().item() < 2e-2
+
+
+def test_reference_pipeline_drives_the_product_modules(monkeypatch):
+    from easyanimate_b200.autoencoder_magvit import AutoencoderKLMagvit
+    from easyanimate_b200.transformer3d import EasyAnimateTransformer3DModel
+    cpu_ops.install(monkeypatch)
+    cpu_ops.install_vae(monkeypatch)
+
+    def decode_on_cpu(self, z):  # the product refuses CPU latents (no CPU path); the host logic under test starts behind that guard
+        outs = [self._decode_one(zb) for zb in z.to(bf16)]
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+
+    monkeypatch.setattr(AutoencoderKLMagvit, "_decode", decode_on_cpu)
+    lat, pe, ne = (t.to(bf16) for t in _inputs(7))
+    ob = dit.init_weights_(dit.OracleTransformer3D(**CFG), 31).to(bf16)
+    ours_t = EasyAnimateTransformer3DModel(**CFG, time_position_encoding_type="3d_rope").to(bf16)
+    ours_t.load_state_dict(ob.state_dict(), strict=True)
+    ov = vae.init_weights_(vae.OracleAutoencoderKLMagvit(block_out_channels=list(BOC)), 32).to(bf16)
+    ours_v = AutoencoderKLMagvit(latent_channels=16, cache_mag_vae=True, spatial_group_norm=True,
+                                 mid_block_attention_type="spatial", block_out_channels=list(BOC), scaling_factor=0.7125).to(bf16)
+    ours_v.load_state_dict(ov.state_dict(), strict=False)
+    pipe = ref_pipeline.reference_pipeline(ours_t, ours_v)
+    frames = ref_pipeline.run(pipe, lat, pe, ne, height=H, width=W, video_length=FRAMES, num_inference_steps=STEPS)
+    rt, rv = _reference_modules(bf16)
+    want = ref_pipeline.run(ref_pipeline.reference_pipeline(rt, rv), lat, pe, ne, height=H, width=W, video_length=FRAMES,
+                            num_inference_steps=STEPS)
+    assert frames.shape == want.shape == (1, 3, FRAMES, H, W) and frames.dtype == torch.float32
+    rel = ((frames - want).norm() / want.norm()).item()
+    assert rel < 3e-2, rel  # bf16 round-off of two op orders through 3 CFG steps + decode; a plumbing error is O(1)
