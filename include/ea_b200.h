@@ -205,7 +205,7 @@ int ea_dequant_e4m3(const void* w8, void* w16, int64_t n, void* stream);
  *     5/6 = 1/2 of 4 in two phases; bit11 (0x800): P packed by truncation instead of round-to-nearest;
  *     bit13 (0x2000): three query tiles per CTA and 64-key blocks (three softmax warps per SM sub-partition); there the
  *     polynomial code 4 / 7 means 1 of every 8 / 16 pairs - 0x217c is the Python layer's default;
- *     bit14 (0x4000): four query tiles and 32-key blocks (experimental).
+ *     bit14 (0x4000): rejected (a four-tile x 32-key layout, withdrawn after it deadlocked on B200).
  *   Other values select retired generations (first: bits 0-1, fourth: 0x0c|poly<<4, ninth: 0x1000|...), present only in an
  *   A/B build (EA_ATTN_AB=1 build.sh; tools/attn_ab/); ea_attn_generations() returns the bitmask of generations built
  *   in (bit 6 always).  Anything else is EA_ERR_INVALID. */
