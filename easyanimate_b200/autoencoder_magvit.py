@@ -250,6 +250,13 @@ class _Encoder(nn.Module):  # omnigen_enc_dec.py:24-337
         return self.conv_out.run(x, out_planar=True)
 
 
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    """There is no CPU path: decode / encode refuse host tensors.  (One function so that the CPU host-logic tests, which swap
+    the kernels for torch stand-ins, can lift exactly this guard and nothing else.)"""
+    if not t.is_cuda:
+        raise L.EaError(f"easyanimate_b200 has no CPU path: {what} must be on a CUDA device")
+
+
 class AutoencoderKLMagvit(nn.Module, ConfigMixinLite):
     _supports_gradient_checkpointing = False
 
@@ -419,8 +426,7 @@ class AutoencoderKLMagvit(nn.Module, ConfigMixinLite):
             raise NotImplementedError("upcast_vae (fp32 decode) is not implemented: easyanimate_b200 computes in bf16")
         if self.dtype != bf16:
             raise L.EaError("easyanimate_b200 computes in bf16: call .to(torch.bfloat16) on the module first")
-        if not z.is_cuda:
-            raise L.EaError("easyanimate_b200 has no CPU path: latents must be on a CUDA device")
+        _require_cuda(z, "latents")
         z = z.to(bf16)
         tl = self.tile_latent_min_size
         tiled = (self.use_tiling or self.use_tiling_decoder) and (z.shape[-1] > tl or z.shape[-2] > tl)
@@ -506,8 +512,7 @@ class AutoencoderKLMagvit(nn.Module, ConfigMixinLite):
             raise NotImplementedError("upcast_vae (fp32 encode) is not implemented: easyanimate_b200 computes in bf16")
         if self.dtype != bf16:
             raise L.EaError("easyanimate_b200 computes in bf16: call .to(torch.bfloat16) on the module first")
-        if not x.is_cuda:
-            raise L.EaError("easyanimate_b200 has no CPU path: the video must be on a CUDA device")
+        _require_cuda(x, "the video")
         x = x.to(bf16)
         ts = self.tile_sample_min_size
         tiled = (self.use_tiling or self.use_tiling_encoder) and (x.shape[-1] > ts or x.shape[-2] > ts)

@@ -47,18 +47,51 @@ def _reference_pipeline_module():
     return importlib.import_module("easyanimate.pipeline.pipeline_easyanimate")
 
 
+def _tokenizer():
+    # encode_prompt reads tokenizer.model_max_length even when the embeddings are given (pipeline_easyanimate.py:361-363)
+    return types.SimpleNamespace(model_max_length=256)
+
+
+def _scheduler():
+    from diffusers.schedulers import FlowMatchEulerDiscreteScheduler  # real install if present, else the shim
+
+    return FlowMatchEulerDiscreteScheduler(num_train_timesteps=1000, shift=1.0)  # V5.1 scheduler config (shift 1)
+
+
+def reference_inpaint_pipeline(transformer, vae, scheduler=None):
+    """The reference's `EasyAnimateInpaintPipeline` (pipeline_easyanimate_inpaint.py:243-1560; predict_i2v.py builds it), no
+    CLIP image encoder (V5.1: enable_clip_in_inpaint false), text encoders = None."""
+    _reference_pipeline_module()
+    mod = importlib.import_module("easyanimate.pipeline.pipeline_easyanimate_inpaint")
+    return mod.EasyAnimateInpaintPipeline(vae=vae, text_encoder=None, tokenizer=_tokenizer(), text_encoder_2=None, tokenizer_2=None,
+                                          transformer=transformer, scheduler=scheduler or _scheduler())
+
+
+def run_inpaint(pipe, video, mask_video, prompt_embeds, negative_prompt_embeds, *, height, width, num_inference_steps, seed,
+                guidance_scale=6.0, noise_aug_strength=0.0563):
+    """One I2V call the way predict_i2v.py:301-314 makes it (video [B,3,F,H,W] in [0,1], mask_video [B,1,F,H,W] in {0,255}),
+    with precomputed embeddings.  The start noise (and the reference-video noise of add_noise_in_inpaint_model) is drawn from a
+    seeded CPU generator: with a flow-matching scheduler the pipeline cannot take `latents=` (prepare_latents leaves `noise`
+    unbound on that branch, pipeline_easyanimate_inpaint.py:893-905)."""
+    import torch
+
+    ones = torch.ones(prompt_embeds.shape[:2], dtype=torch.long)
+    with torch.no_grad():
+        out = pipe(prompt=None, video_length=video.shape[2], video=video, mask_video=mask_video, height=height, width=width,
+                   num_inference_steps=num_inference_steps, guidance_scale=guidance_scale,
+                   generator=torch.Generator().manual_seed(seed), noise_aug_strength=noise_aug_strength,
+                   prompt_embeds=prompt_embeds, negative_prompt_embeds=negative_prompt_embeds,
+                   prompt_attention_mask=ones, negative_prompt_attention_mask=ones.clone(),
+                   prompt_embeds_2=prompt_embeds, prompt_attention_mask_2=ones.clone(), output_type="latent")
+    return out.frames
+
+
 def reference_pipeline(transformer, vae, scheduler=None):
     """`EasyAnimatePipeline(vae=, transformer=, scheduler=, text encoders = None)` - the reference's class, with whatever
     modules the caller plugs in (the reference's own or the product's).  Prompts must be passed as embeddings."""
     mod = _reference_pipeline_module()
-    if scheduler is None:
-        from diffusers.schedulers import FlowMatchEulerDiscreteScheduler  # real install if present, else the shim
-
-        scheduler = FlowMatchEulerDiscreteScheduler(num_train_timesteps=1000, shift=1.0)  # V5.1 scheduler config (shift 1)
-    # encode_prompt reads tokenizer.model_max_length even when the embeddings are given (pipeline_easyanimate.py:361-363)
-    tokenizer = types.SimpleNamespace(model_max_length=256)
-    return mod.EasyAnimatePipeline(vae=vae, text_encoder=None, tokenizer=tokenizer, text_encoder_2=None, tokenizer_2=None,
-                                   transformer=transformer, scheduler=scheduler)
+    return mod.EasyAnimatePipeline(vae=vae, text_encoder=None, tokenizer=_tokenizer(), text_encoder_2=None, tokenizer_2=None,
+                                   transformer=transformer, scheduler=scheduler or _scheduler())
 
 
 def run(pipe, latents, prompt_embeds, negative_prompt_embeds, *, height, width, video_length, num_inference_steps,

@@ -103,3 +103,59 @@ def test_reference_pipeline_drives_the_product_modules(monkeypatch):
     assert frames.shape == want.shape == (1, 3, FRAMES, H, W) and frames.dtype == torch.float32
     rel = ((frames - want).norm() / want.norm()).item()
     assert rel < 3e-2, rel  # bf16 round-off of two op orders through 3 CFG steps + decode; a plumbing error is O(1)
+
+
+# ---- a17: the I2V path through the reference's own EasyAnimateInpaintPipeline (predict_i2v.py) -------------------------------
+I2V_CFG = dict(CFG, in_channels=33, time_position_encoding_type="3d_rope", resize_inpaint_mask_directly=True,
+               enable_clip_in_inpaint=False, add_noise_in_inpaint_model=True)
+
+
+def _i2v_inputs(seed=9):
+    g = torch.Generator().manual_seed(seed)
+    first = torch.rand(1, 3, 1, H, W, generator=g)
+    video = torch.tile(first, [1, 1, FRAMES, 1, 1])                 # utils.py:105-110: the start image on every frame, in [0, 1]
+    mask = torch.zeros_like(video[:, :1])
+    mask[:, :, 1:] = 255                                             # frame 0 is given, the rest is to be generated
+    pe, ne = torch.randn(1, 9, 128, generator=g) * 3, torch.randn(1, 9, 128, generator=g) * 3
+    return video, mask, pe, ne
+
+
+def test_reference_inpaint_pipeline_drives_the_product_modules(monkeypatch):
+    """`EasyAnimateInpaintPipeline.__call__` (pipeline_easyanimate_inpaint.py:978-1560), unmodified: VaeImageProcessor ->
+    masked video -> `vae.encode(...)[0].mode()` * scaling_factor -> resize_mask -> inpaint_latents (1 + 16 channels) -> denoise
+    loop with `inpaint_latents=` -> decode_latents.  Once over the reference's transformer + VAE, once over the product's
+    (kernels = torch stand-ins): same start noise (seeded generator), same frames up to bf16 round-off."""
+    import easyanimate_b200.autoencoder_magvit as A
+    from easyanimate_b200.transformer3d import EasyAnimateTransformer3DModel
+    from oracle import ref_dit, ref_vae
+    cpu_ops.install(monkeypatch)
+    cpu_ops.install_vae(monkeypatch)
+    monkeypatch.setattr(A, "_require_cuda", lambda t, what: None)  # lift the no-CPU-path guard, nothing else
+    video, mask, pe, ne = _i2v_inputs()
+    pe, ne = pe.to(bf16), ne.to(bf16)
+    ocfg = {k: v for k, v in I2V_CFG.items() if k in CFG}
+    ob = dit.init_weights_(dit.OracleTransformer3D(**ocfg), 51).to(bf16)
+    ov = vae.init_weights_(vae.OracleAutoencoderKLMagvit(block_out_channels=list(BOC), with_encoder=True), 52).to(bf16)
+
+    rt = ref_dit.reference_transformer(**I2V_CFG).eval()
+    rt.load_state_dict(ob.state_dict(), strict=True)
+    rv = ref_vae.reference_autoencoder(block_out_channels=BOC).eval()
+    rv.load_state_dict(ov.state_dict(), strict=True)
+    want = ref_pipeline.run_inpaint(ref_pipeline.reference_inpaint_pipeline(rt.to(bf16), rv.to(bf16)), video, mask, pe, ne,
+                                    height=H, width=W, num_inference_steps=STEPS, seed=77)
+
+    ours_t = EasyAnimateTransformer3DModel(**I2V_CFG).to(bf16)
+    ours_t.load_state_dict(ob.state_dict(), strict=True)
+    ours_v = A.AutoencoderKLMagvit(latent_channels=16, cache_mag_vae=True, spatial_group_norm=True, mid_block_attention_type="spatial",
+                                   block_out_channels=list(BOC), scaling_factor=0.7125, mini_batch_encoder=4,
+                                   mini_batch_decoder=1).to(bf16)
+    ours_v.load_state_dict(ov.state_dict(), strict=True)
+    seen = {}
+    enc = ours_v.encode
+    ours_v.encode = lambda x, *a, **k: (seen.setdefault("encode_calls", []).append(tuple(x.shape)), enc(x, *a, **k))[1]
+    frames = ref_pipeline.run_inpaint(ref_pipeline.reference_inpaint_pipeline(ours_t, ours_v), video, mask, pe, ne,
+                                      height=H, width=W, num_inference_steps=STEPS, seed=77)
+    assert seen["encode_calls"] == [(1, 3, FRAMES, H, W)]  # the masked video, once (resize_inpaint_mask_directly: no mask encode)
+    assert frames.shape == want.shape == (1, 3, FRAMES, H, W) and frames.dtype == torch.float32
+    rel = ((frames - want).norm() / want.norm()).item()
+    assert rel < 3e-2, rel
