@@ -14,3 +14,6 @@ class AutoencoderKL:  # imported by easyanimate/models/autoencoder_magvit.py:41,
         raise NotImplementedError("diffusers shim: AutoencoderKL is a placeholder")
 
 from .pipelines.pipeline_utils import DiffusionPipeline  # noqa: E402  (pipeline_easyanimate.py:22)
+from .models._placeholder import placeholder as _placeholder  # noqa: E402
+
+ImagePipelineOutput = _placeholder("ImagePipelineOutput")  # pipeline_easyanimate_control.py:24

@@ -12,6 +12,7 @@ from ..configuration_utils import FrozenDict
 from ..models._placeholder import placeholder
 
 DDIMScheduler = placeholder("DDIMScheduler")
+DPMSolverMultistepScheduler = placeholder("DPMSolverMultistepScheduler")
 
 
 class FlowMatchEulerDiscreteScheduler:

@@ -67,6 +67,30 @@ def reference_inpaint_pipeline(transformer, vae, scheduler=None):
                                           transformer=transformer, scheduler=scheduler or _scheduler())
 
 
+def reference_control_pipeline(transformer, vae, scheduler=None):
+    """The reference's `EasyAnimateControlPipeline` (pipeline_easyanimate_control.py:214-1290; predict_v2v_control.py builds it)."""
+    _reference_pipeline_module()
+    mod = importlib.import_module("easyanimate.pipeline.pipeline_easyanimate_control")
+    return mod.EasyAnimateControlPipeline(vae=vae, text_encoder=None, tokenizer=_tokenizer(), text_encoder_2=None, tokenizer_2=None,
+                                          transformer=transformer, scheduler=scheduler or _scheduler())
+
+
+def run_control(pipe, latents, control_video, ref_image, prompt_embeds, negative_prompt_embeds, *, height, width, video_length,
+                num_inference_steps, guidance_scale=6.0):
+    """One Control call the way predict_v2v_control.py makes it: control_video [B,3,F,H,W] in [0,1] (pose / depth / canny
+    frames), ref_image [B,3,1,H,W] in [0,1] or None, precomputed embeddings, given start latents."""
+    import torch
+
+    ones = torch.ones(prompt_embeds.shape[:2], dtype=torch.long)
+    with torch.no_grad():
+        out = pipe(prompt=None, video_length=video_length, control_video=control_video, ref_image=ref_image, height=height,
+                   width=width, num_inference_steps=num_inference_steps, guidance_scale=guidance_scale, latents=latents,
+                   prompt_embeds=prompt_embeds, negative_prompt_embeds=negative_prompt_embeds,
+                   prompt_attention_mask=ones, negative_prompt_attention_mask=ones.clone(),
+                   prompt_embeds_2=prompt_embeds, prompt_attention_mask_2=ones.clone(), output_type="latent")
+    return out.frames
+
+
 def run_inpaint(pipe, video, mask_video, prompt_embeds, negative_prompt_embeds, *, height, width, num_inference_steps, seed,
                 guidance_scale=6.0, noise_aug_strength=0.0563):
     """One I2V call the way predict_i2v.py:301-314 makes it (video [B,3,F,H,W] in [0,1], mask_video [B,1,F,H,W] in {0,255}),

@@ -159,3 +159,46 @@ def test_reference_inpaint_pipeline_drives_the_product_modules(monkeypatch):
     assert frames.shape == want.shape == (1, 3, FRAMES, H, W) and frames.dtype == torch.float32
     rel = ((frames - want).norm() / want.norm()).item()
     assert rel < 3e-2, rel
+
+
+# ---- f4: the Control path through the reference's own EasyAnimateControlPipeline ---------------------------------------------
+CONTROL_CFG = dict(CFG, in_channels=48, time_position_encoding_type="3d_rope", add_ref_latent_in_control_model=True)
+
+
+@pytest.mark.parametrize("with_ref_image", [True, False])
+def test_reference_control_pipeline_drives_the_product_modules(monkeypatch, with_ref_image):
+    """`EasyAnimateControlPipeline.__call__` (pipeline_easyanimate_control.py:830-1290), unmodified: control video ->
+    `vae.encode` -> control_latents (16 channels) + the reference image's latent in frame 0 of 16 more channels
+    (add_ref_latent_in_control_model) -> `transformer(..., control_latents=)` -> decode_latents."""
+    import easyanimate_b200.autoencoder_magvit as A
+    from easyanimate_b200.transformer3d import EasyAnimateTransformer3DModel
+    from oracle import ref_dit, ref_vae
+    cpu_ops.install(monkeypatch)
+    cpu_ops.install_vae(monkeypatch)
+    monkeypatch.setattr(A, "_require_cuda", lambda t, what: None)
+    g = torch.Generator().manual_seed(13)
+    lat = torch.randn(1, 16, LF, H // 8, W // 8, generator=g).to(bf16)
+    control = torch.rand(1, 3, FRAMES, H, W, generator=g)
+    ref_image = torch.rand(1, 3, 1, H, W, generator=g) if with_ref_image else None
+    pe, ne = (torch.randn(1, 9, 128, generator=g) * 3).to(bf16), (torch.randn(1, 9, 128, generator=g) * 3).to(bf16)
+    ocfg = {k: v for k, v in CONTROL_CFG.items() if k in CFG}
+    ob = dit.init_weights_(dit.OracleTransformer3D(**ocfg), 61).to(bf16)
+    ov = vae.init_weights_(vae.OracleAutoencoderKLMagvit(block_out_channels=list(BOC), with_encoder=True), 62).to(bf16)
+    kw = dict(height=H, width=W, video_length=FRAMES, num_inference_steps=STEPS)
+
+    rt = ref_dit.reference_transformer(**CONTROL_CFG).eval()
+    rt.load_state_dict(ob.state_dict(), strict=True)
+    rv = ref_vae.reference_autoencoder(block_out_channels=BOC).eval()
+    rv.load_state_dict(ov.state_dict(), strict=True)
+    want = ref_pipeline.run_control(ref_pipeline.reference_control_pipeline(rt.to(bf16), rv.to(bf16)), lat, control, ref_image,
+                                    pe, ne, **kw)
+    ours_t = EasyAnimateTransformer3DModel(**CONTROL_CFG).to(bf16)
+    ours_t.load_state_dict(ob.state_dict(), strict=True)
+    ours_v = A.AutoencoderKLMagvit(latent_channels=16, cache_mag_vae=True, spatial_group_norm=True, mid_block_attention_type="spatial",
+                                   block_out_channels=list(BOC), scaling_factor=0.7125, mini_batch_encoder=4,
+                                   mini_batch_decoder=1).to(bf16)
+    ours_v.load_state_dict(ov.state_dict(), strict=True)
+    frames = ref_pipeline.run_control(ref_pipeline.reference_control_pipeline(ours_t, ours_v), lat, control, ref_image, pe, ne, **kw)
+    assert frames.shape == want.shape == (1, 3, FRAMES, H, W) and frames.dtype == torch.float32
+    rel = ((frames - want).norm() / want.norm()).item()
+    assert rel < 3e-2, rel
