@@ -6,11 +6,14 @@ importing this package requires the in-tree CUDA library ``libea_b200.so`` (ther
 from . import _lib  # noqa: F401  (fails loudly if the CUDA extension has not been built)
 from .autoencoder_magvit import AutoencoderKLMagvit
 from .pipeline import EasyAnimateSampler, rope_table
+from .pipelines import (EasyAnimateControlPipeline, EasyAnimateInpaintPipeline, EasyAnimatePipeline,
+                        EasyAnimatePipelineOutput)
 from .scheduler import FlowMatchEulerDiscreteScheduler
 from .transformer3d import EasyAnimateTransformer3DModel
 
 name_to_transformer3d = {"EasyAnimateTransformer3DModel": EasyAnimateTransformer3DModel}
 name_to_autoencoder_magvit = {"AutoencoderKLMagvit": AutoencoderKLMagvit}
 
-__all__ = ["AutoencoderKLMagvit", "EasyAnimateSampler", "EasyAnimateTransformer3DModel", "FlowMatchEulerDiscreteScheduler",
+__all__ = ["AutoencoderKLMagvit", "EasyAnimateControlPipeline", "EasyAnimateInpaintPipeline", "EasyAnimatePipeline",
+           "EasyAnimatePipelineOutput", "EasyAnimateSampler", "EasyAnimateTransformer3DModel", "FlowMatchEulerDiscreteScheduler",
            "name_to_autoencoder_magvit", "name_to_transformer3d", "rope_table"]

@@ -95,26 +95,32 @@ class EasyAnimateSampler:
         return self.scheduler.timesteps
 
     # -- one scheduler step ------------------------------------------------------------------------------------
-    def step(self, latents: torch.Tensor, i: int, embeds: torch.Tensor, rope, inpaint_latents=None) -> torch.Tensor:
+    def step(self, latents: torch.Tensor, i: int, embeds: torch.Tensor, rope, inpaint_latents=None, control_latents=None) -> torch.Tensor:
         """latents [B,C,F,h,w]; embeds [2B,S_t,E] = cat(negative, positive) when CFG is on (pipeline_easyanimate.py:1052-1056).
-        inpaint_latents: [B,...] (the same conditioning for both branches, what pipeline_easyanimate_inpaint.py:1496-1511
-        builds with cat([x] * 2)) or [2B,...] = cat(unconditional-branch, text-branch) conditioning."""
+        inpaint_latents / control_latents: [B,...] (the same conditioning for both branches, what
+        pipeline_easyanimate_inpaint.py:1496-1511 and pipeline_easyanimate_control.py:1066-1125 build with cat([x] * 2)) or
+        [2B,...] = cat(unconditional-branch, text-branch) conditioning."""
         t = self.scheduler.timesteps[i]
         sigma, sigma_next = self.scheduler.sigma_pair(i)
         B = latents.shape[0]
+        extra = {}  # keyword only when given: the plain text-to-video call stays exactly the call the GPU suite validated
         if not self.do_cfg:
+            if control_latents is not None:
+                extra["control_latents"] = control_latents
             t_expand = t.reshape(1).expand(B).to(device=latents.device, dtype=bf16)
             pred = self.transformer(latents, t_expand, encoder_hidden_states=embeds, image_rotary_emb=rope,
-                                    inpaint_latents=inpaint_latents, return_dict=False)[0]
+                                    inpaint_latents=inpaint_latents, return_dict=False, **extra)[0]
             return self._euler(pred, latents, 1.0, sigma, sigma_next, use_cfg=False)
         if self.cfg_group is None:
             latent_in = torch.cat([latents] * 2)
             inp = inpaint_latents
             if inp is not None and inp.shape[0] == B:
                 inp = torch.cat([inp] * 2)
+            if control_latents is not None:
+                extra["control_latents"] = torch.cat([control_latents] * 2) if control_latents.shape[0] == B else control_latents
             t_expand = t.reshape(1).expand(2 * B).to(device=latents.device, dtype=bf16)
             pred = self.transformer(latent_in, t_expand, encoder_hidden_states=embeds, image_rotary_emb=rope,
-                                    inpaint_latents=inp, return_dict=False)[0]
+                                    inpaint_latents=inp, return_dict=False, **extra)[0]
         else:
             import torch.distributed as dist
             r = self._cfg_rank  # rank 0: unconditional branch, rank 1: text-conditioned branch
@@ -122,8 +128,11 @@ class EasyAnimateSampler:
             inp = inpaint_latents
             if inp is not None and inp.shape[0] == 2 * B:
                 inp = inp[r * B:(r + 1) * B].contiguous()
+            if control_latents is not None:
+                extra["control_latents"] = (control_latents[r * B:(r + 1) * B].contiguous() if control_latents.shape[0] == 2 * B
+                                            else control_latents)
             mine = self.transformer(latents, t_expand, encoder_hidden_states=embeds[r * B:(r + 1) * B].contiguous(),
-                                    image_rotary_emb=rope, inpaint_latents=inp, return_dict=False)[0]
+                                    image_rotary_emb=rope, inpaint_latents=inp, return_dict=False, **extra)[0]
             pred = torch.empty((2 * B,) + tuple(mine.shape[1:]), device=mine.device, dtype=mine.dtype)
             dist.all_gather_into_tensor(pred, mine.contiguous(), group=self.cfg_group)
         return self._euler(pred, latents, self.guidance_scale, sigma, sigma_next, use_cfg=True)

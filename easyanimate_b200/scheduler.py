@@ -87,5 +87,17 @@ class FlowMatchEulerDiscreteScheduler:
         self._step_index += 1
         return (prev,) if not return_dict else FrozenConfig(prev_sample=prev)
 
+    def scale_noise(self, sample: torch.Tensor, timestep, noise: torch.Tensor, index: Optional[int] = None) -> torch.Tensor:
+        """diffusers' `scale_noise` (the start of a strength < 1 image-to-video / video-to-video call,
+        pipeline_easyanimate_inpaint.py:896): sigma * noise + (1 - sigma) * sample with sigma rounded to the sample's dtype and
+        tensor ops in that dtype.  One-off preparation before the loop (torch ops)."""
+        if index is None:
+            ts = [float(x) for x in self.timesteps.cpu()]
+            t0 = float(torch.as_tensor(timestep).reshape(-1)[0])
+            hits = [i for i, v in enumerate(ts) if v == t0]
+            index = hits[1 if len(hits) > 1 else 0]
+        sigma = self.sigmas[index].to(device=sample.device, dtype=sample.dtype)
+        return sigma * noise + (1.0 - sigma) * sample
+
     def sigma_pair(self, i: int):
         return self._sigmas_host[i], self._sigmas_host[i + 1]

@@ -63,6 +63,27 @@ class FlowMatchEulerDiscreteScheduler:
         self._step_index = None
         self._begin_index = None
 
+    @property
+    def begin_index(self):
+        return self._begin_index
+
+    def scale_noise(self, sample, timestep, noise=None):
+        """Forward process of flow matching at `timestep`: sigma * noise + (1 - sigma) * sample, in the SAMPLE's dtype (the sigma
+        table is cast to it first) - called by the inpaint pipeline for strength < 1 (pipeline_easyanimate_inpaint.py:896)."""
+        sigmas = self.sigmas.to(device=sample.device, dtype=sample.dtype)
+        schedule_timesteps = self.timesteps.to(sample.device)
+        timestep = timestep.to(sample.device)
+        if self.begin_index is None:
+            step_indices = [self.index_for_timestep(t, schedule_timesteps) for t in timestep]
+        elif self.step_index is not None:
+            step_indices = [self.step_index] * timestep.shape[0]
+        else:
+            step_indices = [self.begin_index] * timestep.shape[0]
+        sigma = sigmas[step_indices].flatten()
+        while len(sigma.shape) < len(sample.shape):
+            sigma = sigma.unsqueeze(-1)
+        return sigma * noise + (1.0 - sigma) * sample
+
     def index_for_timestep(self, timestep, schedule_timesteps=None):
         if schedule_timesteps is None:
             schedule_timesteps = self.timesteps

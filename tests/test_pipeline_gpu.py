@@ -189,6 +189,27 @@ def test_sampler_and_decode_match_the_reference_pipeline_call():
     three_way(frames_ref_z, t["frames_bf16"], t["frames_fp32"], name="reference_pipeline_decode_of_reference_latents")
 
 
+@gpu
+def test_native_pipeline_call_matches_the_reference_pipeline_call():
+    """easyanimate_b200.EasyAnimatePipeline.__call__ (the reference's signature, no diffusers) on the GPU: same keyword arguments
+    the reference's call was minted with -> the same frames as sampler.sample + decode_latents, bit for bit, and within the
+    three-way criterion of the reference's own frames."""
+    from easyanimate_b200 import EasyAnimatePipeline
+    t, meta, sampler = prelude_reference_pipeline_golden()
+    h, w, steps, frames_n = int(meta["height"]), int(meta["width"]), int(meta["steps"]), int(meta["video_length"])
+    pe, ne = t["prompt_embeds"], t["negative_prompt_embeds"]
+    ones = torch.ones(pe.shape[:2], dtype=torch.long)
+    pipe = EasyAnimatePipeline(vae=sampler.vae, transformer=sampler.transformer)
+    out = pipe(video_length=frames_n, height=h, width=w, num_inference_steps=steps, guidance_scale=float(meta["guidance_scale"]),
+               latents=t["latents"], prompt_embeds=pe, negative_prompt_embeds=ne, prompt_attention_mask=ones,
+               negative_prompt_attention_mask=ones.clone(), prompt_embeds_2=pe, prompt_attention_mask_2=ones.clone())
+    frames = out.frames
+    assert isinstance(frames, torch.Tensor) and frames.dtype == torch.float32 and not frames.is_cuda
+    three_way(frames, t["frames_bf16"], t["frames_fp32"], slack=2.0, name="native_pipeline_frames")
+    z = sampler.sample(t["latents"].cuda(), pe.cuda(), ne.cuda(), height=h, width=w, num_inference_steps=steps)
+    assert torch.equal(frames, sampler.decode_latents(z))
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # a17 / boundary: checkpoint loaders
 # ---------------------------------------------------------------------------------------------------------------
