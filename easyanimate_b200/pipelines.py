@@ -133,6 +133,14 @@ class _B200PipelineBase:
     def _execution_device(self):
         return next(self.transformer.parameters()).device
 
+    @property
+    def _dtype(self):
+        """pipeline_easyanimate.py:906-911: the text encoder's dtype when there is one, else the transformer's."""
+        for m in (self.text_encoder, self.text_encoder_2):
+            if m is not None:
+                return m.dtype
+        return self.transformer.dtype
+
     def to(self, device):
         self.transformer.to(device)
         self.vae.to(device)
@@ -326,7 +334,7 @@ class _B200PipelineBase:
 
     def _embeds(self, prompt, negative_prompt, num_images_per_prompt, prompt_embeds, negative_prompt_embeds, prompt_attention_mask,
                 negative_prompt_attention_mask):
-        device, dtype = self._execution_device, self.transformer.dtype
+        device, dtype = self._execution_device, self._dtype
         return self.encode_prompt(prompt=prompt, device=device, dtype=dtype, num_images_per_prompt=num_images_per_prompt,
                                   do_classifier_free_guidance=self.do_classifier_free_guidance, negative_prompt=negative_prompt,
                                   prompt_embeds=prompt_embeds, negative_prompt_embeds=negative_prompt_embeds,
@@ -365,7 +373,7 @@ class EasyAnimatePipeline(_B200PipelineBase):
             prompt_attention_mask_2=prompt_attention_mask_2, negative_prompt_attention_mask_2=negative_prompt_attention_mask_2,
             callback_on_step_end_tensor_inputs=callback_on_step_end_tensor_inputs))
         batch = self._batch_size(prompt, prompt_embeds)
-        device, dtype = self._execution_device, self.transformer.dtype
+        device, dtype = self._execution_device, self._dtype
         pe, ne, _, _ = self._embeds(prompt, negative_prompt, num_images_per_prompt, prompt_embeds, negative_prompt_embeds,
                                     prompt_attention_mask, negative_prompt_attention_mask)
         first, steps = self._set_timesteps(num_inference_steps, timesteps)
@@ -435,7 +443,7 @@ class EasyAnimateInpaintPipeline(_B200PipelineBase):
         if clip_image is not None and getattr(self.transformer, "enable_clip_in_inpaint", False):
             raise NotImplementedError("the CLIP-image branch (enable_clip_in_inpaint) is not carried over (V5.1 does not use it)")
         batch = self._batch_size(prompt, prompt_embeds) * num_images_per_prompt
-        device, dtype = self._execution_device, self.transformer.dtype
+        device, dtype = self._execution_device, self._dtype
         pe, ne, _, _ = self._embeds(prompt, negative_prompt, num_images_per_prompt, prompt_embeds, negative_prompt_embeds,
                                     prompt_attention_mask, negative_prompt_attention_mask)
         first, steps = self._set_timesteps(num_inference_steps, timesteps, strength)
@@ -495,7 +503,7 @@ class EasyAnimateControlPipeline(_B200PipelineBase):
             prompt_attention_mask_2=prompt_attention_mask_2, negative_prompt_attention_mask_2=negative_prompt_attention_mask_2,
             callback_on_step_end_tensor_inputs=callback_on_step_end_tensor_inputs))
         batch = self._batch_size(prompt, prompt_embeds) * num_images_per_prompt
-        device, dtype = self._execution_device, self.transformer.dtype
+        device, dtype = self._execution_device, self._dtype
         pe, ne, _, _ = self._embeds(prompt, negative_prompt, num_images_per_prompt, prompt_embeds, negative_prompt_embeds,
                                     prompt_attention_mask, negative_prompt_attention_mask)
         first, steps = self._set_timesteps(num_inference_steps, timesteps)

@@ -184,3 +184,65 @@ def test_control_pipeline_equals_the_reference_pipeline(on_cpu, mode):
         kw["control_camera_video"] = torch.randn(1, 16, FRAMES, H, W, generator=g)
     want = ref_pipeline.reference_control_pipeline(t, v)(**kw).frames
     _same(EasyAnimateControlPipeline(vae=v, transformer=t)(**kw).frames, want)
+
+
+class _FakeTokens(dict):
+    input_ids = property(lambda self: self["input_ids"])
+    attention_mask = property(lambda self: self["attention_mask"])
+
+    def to(self, device):
+        return self
+
+
+class _FakeTokenizer:
+    """Just enough of Qwen2Tokenizer for encode_prompt's LLM branch: a chat template and fixed-length 'tokens' (byte values)."""
+    model_max_length = 32
+
+    def apply_chat_template(self, messages, tokenize=False, add_generation_prompt=True):
+        assert not tokenize and add_generation_prompt
+        return "".join(f"<|user|>{m['content'][0]['text']}" for m in messages) + "<|assistant|>"
+
+    def __call__(self, text, padding, max_length, truncation, return_attention_mask, padding_side, return_tensors):
+        assert padding == "max_length" and truncation and return_attention_mask and padding_side == "right" and return_tensors == "pt"
+        ids, mask = [], []
+        for s in text:
+            b = list(s.encode())[:max_length]
+            ids.append(b + [0] * (max_length - len(b)))
+            mask.append([1] * len(b) + [0] * (max_length - len(b)))
+        return _FakeTokens(input_ids=torch.tensor(ids), attention_mask=torch.tensor(mask))
+
+
+class _FakeTextEncoder(torch.nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.emb = torch.nn.Embedding(256, dim)
+        self.mix = torch.nn.Linear(dim, dim)
+
+    dtype = property(lambda self: self.emb.weight.dtype)
+    device = property(lambda self: self.emb.weight.device)
+
+    def forward(self, input_ids, attention_mask, output_hidden_states):
+        assert output_hidden_states
+        h0 = self.emb(input_ids) * attention_mask[..., None].to(self.dtype)
+        h1 = self.mix(h0)
+        return type("Out", (), {"hidden_states": [h0, h1, self.mix(h1)]})()
+
+
+def test_prompt_strings_go_through_the_llm_branch_like_the_reference(on_cpu):
+    """prompt / negative_prompt as strings: chat template -> tokenizer -> text_encoder(...).hidden_states[-2] -> the loop."""
+    from easyanimate_b200 import EasyAnimatePipeline
+    t, v = _modules(on_cpu)
+    torch.manual_seed(0)
+    tok, enc = _FakeTokenizer(), _FakeTextEncoder(128).to(bf16)
+    ref = ref_pipeline.reference_pipeline(t, v)
+    ref.tokenizer, ref.text_encoder = tok, enc
+    lat = torch.randn(1, 16, LF, H // 8, W // 8, generator=torch.Generator().manual_seed(11)).to(bf16)
+    kw = dict(prompt="a corgi surfing", negative_prompt="blurry", video_length=FRAMES, height=H, width=W, num_inference_steps=2,
+              guidance_scale=6.0, latents=lat)
+    want = ref(**kw).frames
+    got = EasyAnimatePipeline(vae=v, transformer=t, tokenizer=tok, text_encoder=enc)(**kw).frames
+    _same(got, want)
+    e_ref = ref.encode_prompt("a corgi surfing", torch.device("cpu"), bf16, negative_prompt="blurry")
+    e_ours = EasyAnimatePipeline(vae=v, transformer=t, tokenizer=tok, text_encoder=enc).encode_prompt(
+        "a corgi surfing", torch.device("cpu"), bf16, negative_prompt="blurry")
+    assert all(torch.equal(a, b) for a, b in zip(e_ref, e_ours))
