@@ -172,3 +172,68 @@ def test_teacache_with_cfg_parallel_takes_the_joint_batch_decision():
     assert skipped >= 1, "the test must exercise the cached path"
     assert res[0][1] == res[1][1] == skipped, (res[0][1], res[1][1], skipped)
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][0], single)
+
+
+# ---- the native pipeline call (easyanimate_b200.pipelines) on a CFG pair: same frames on both ranks and as one process ----
+class _PipeTransformer(FakeTransformer):
+    def __init__(self):
+        super().__init__()
+        from easyanimate_b200.config import FrozenConfig
+        self.w = torch.nn.Parameter(torch.zeros(1, dtype=bf16))
+        self.config = FrozenConfig(in_channels=4, attention_head_dim=64, patch_size=2, enable_text_attention_mask=True)
+
+    dtype = property(lambda self: self.w.dtype)
+
+
+class _PipeVae(torch.nn.Module):
+    cache_mag_vae, mini_batch_encoder, mini_batch_decoder = True, 4, 1
+
+    def __init__(self):
+        super().__init__()
+        from easyanimate_b200.config import FrozenConfig
+        self.config = FrozenConfig(block_out_channels=[8, 8, 8, 8], scaling_factor=0.5, latent_channels=4)
+
+    def decode_scaled(self, latents, out=None, dtype=torch.float32, to_host=True):
+        return (latents.float() / self.config.scaling_factor).clamp(-1, 1).mul(0.5).add(0.5).repeat_interleave(2, dim=1)[:, :3]
+
+
+def _pipeline_call(cfg_group=None):
+    from easyanimate_b200 import ops
+    from easyanimate_b200.pipelines import EasyAnimatePipeline
+    g = torch.Generator().manual_seed(3)
+    pe, ne = torch.randn(1, 3, 8, generator=g).to(bf16), torch.randn(1, 3, 8, generator=g).to(bf16)
+    ones = torch.ones(1, 3, dtype=torch.long)
+    pipe = EasyAnimatePipeline(vae=_PipeVae(), transformer=_PipeTransformer(), cfg_group=cfg_group)
+    real, ops.cfg_euler_step = ops.cfg_euler_step, euler_cpu  # the sampler binds the CFG + Euler kernel at construction
+    try:
+        return pipe(video_length=5, height=32, width=32, num_inference_steps=3, guidance_scale=6.0,
+                    generator=torch.Generator().manual_seed(4), prompt_embeds=pe, negative_prompt_embeds=ne,
+                    prompt_attention_mask=ones, negative_prompt_attention_mask=ones, prompt_embeds_2=pe,
+                    prompt_attention_mask_2=ones).frames
+    finally:
+        ops.cfg_euler_step = real
+
+
+def _pipe_worker(rank, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE="2")
+    dist.init_process_group("gloo", rank=rank, world_size=2)
+    frames = _pipeline_call(dist.new_group([0, 1]))
+    q.put((rank, frames))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_native_pipeline_call_on_a_cfg_pair_matches_single_process():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30100 + (os.getpid() % 400)
+    procs = [ctx.Process(target=_pipe_worker, args=(r, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref = _pipeline_call()
+    assert ref.shape == (1, 3, 2, 4, 4)
+    assert torch.equal(got[0], got[1]) and torch.equal(got[0], ref)
