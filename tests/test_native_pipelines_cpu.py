@@ -246,3 +246,23 @@ def test_prompt_strings_go_through_the_llm_branch_like_the_reference(on_cpu):
     e_ours = EasyAnimatePipeline(vae=v, transformer=t, tokenizer=tok, text_encoder=enc).encode_prompt(
         "a corgi surfing", torch.device("cpu"), bf16, negative_prompt="blurry")
     assert all(torch.equal(a, b) for a, b in zip(e_ref, e_ours))
+
+
+def test_teacache_inside_the_pipeline_call_matches_the_reference_pipeline(on_cpu):
+    """predict_t2v.py:275-278 enables TeaCache on the transformer before calling the pipeline: the skip decisions are taken
+    inside `transformer.forward`, so both pipelines see the same cached / computed steps and the same frames."""
+    from easyanimate_b200 import EasyAnimatePipeline
+    t, v = _modules(on_cpu)
+    coeffs = [1.07862322, -4.19362456, 3.06725828, 0.33161686, 0.02374758]
+    g = torch.Generator().manual_seed(21)
+    lat = torch.randn(1, 16, LF, H // 8, W // 8, generator=g).to(bf16)
+    pe, ne = _embeds(g)
+    steps = 8
+    kw = dict(video_length=FRAMES, height=H, width=W, num_inference_steps=steps, guidance_scale=6.0, latents=lat, **_mask_kw(pe, ne))
+    t.enable_teacache(steps, 0.3, coefficients=coeffs)
+    want = ref_pipeline.reference_pipeline(t, v)(**kw).frames
+    skipped_ref = t.teacache.skipped
+    assert t.teacache.cnt == 0  # wrapped around after `steps` calls: ready for the next video
+    got = EasyAnimatePipeline(vae=v, transformer=t)(**kw).frames
+    assert 0 < skipped_ref < steps and t.teacache.skipped == 2 * skipped_ref
+    _same(got, want)
