@@ -139,7 +139,8 @@ class _B200PipelineBase:
         for m in (self.text_encoder, self.text_encoder_2):
             if m is not None:
                 return m.dtype
-        return self.transformer.dtype
+        d = self.transformer.dtype
+        return bf16 if d == torch.float8_e4m3fn else d  # fp8 weight STORAGE computes in bf16 (transformer3d.py)
 
     def to(self, device):
         self.transformer.to(device)
