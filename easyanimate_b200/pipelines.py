@@ -1,8 +1,8 @@
 """The reference's three pipeline entry points with their call signatures, on the B200 modules and WITHOUT diffusers:
 
-    EasyAnimatePipeline          easyanimate/pipeline/pipeline_easyanimate.py:170-1160          (predict_t2v.py)
-    EasyAnimateInpaintPipeline   easyanimate/pipeline/pipeline_easyanimate_inpaint.py:243-1560  (predict_i2v.py, predict_v2v.py)
-    EasyAnimateControlPipeline   easyanimate/pipeline/pipeline_easyanimate_control.py:214-1290  (predict_v2v_control.py)
+    EasyAnimatePipeline          easyanimate/pipeline/pipeline_easyanimate.py:175-1148          (predict_t2v.py)
+    EasyAnimateInpaintPipeline   easyanimate/pipeline/pipeline_easyanimate_inpaint.py:245-1604  (predict_i2v.py, predict_v2v.py)
+    EasyAnimateControlPipeline   easyanimate/pipeline/pipeline_easyanimate_control.py:200-1282  (predict_v2v_control.py)
 
 The reference's own pipeline classes accept the B200 transformer / VAE objects unchanged (tested by
 tests/test_ref_pipeline_cpu.py); these classes are for deployments that do not install diffusers, and they run the loop the
@@ -350,7 +350,7 @@ class _B200PipelineBase:
 
 
 class EasyAnimatePipeline(_B200PipelineBase):
-    """Text-to-video: pipeline_easyanimate.py:764-1160."""
+    """Text-to-video: pipeline_easyanimate.py:769-1148."""
 
     @torch.no_grad()
     def __call__(self, prompt: Union[str, List[str]] = None, video_length: Optional[int] = None, height: Optional[int] = None,
@@ -387,7 +387,7 @@ class EasyAnimatePipeline(_B200PipelineBase):
 
 class EasyAnimateInpaintPipeline(_B200PipelineBase):
     """Image-to-video / video-to-video with the InP transformer (33 input channels = 16 latent + 1 mask + 16 masked-video
-    latents): pipeline_easyanimate_inpaint.py:978-1560."""
+    latents): pipeline_easyanimate_inpaint.py:978-1604."""
 
     def _inpaint_latents(self, latents, init_video, mask_video, masked_video_latents, height, width, generator,
                          noise_aug_strength, device, dtype):
@@ -478,7 +478,7 @@ class EasyAnimateInpaintPipeline(_B200PipelineBase):
 
 
 class EasyAnimateControlPipeline(_B200PipelineBase):
-    """Control (pose / depth / canny video, camera trajectories, reference image): pipeline_easyanimate_control.py:830-1290."""
+    """Control (pose / depth / canny video, camera trajectories, reference image): pipeline_easyanimate_control.py:833-1282."""
 
     @torch.no_grad()
     def __call__(self, prompt: Union[str, List[str]] = None, video_length: Optional[int] = None, height: Optional[int] = None,

@@ -1,5 +1,5 @@
 """ORACLE helper (test infrastructure only): the reference's own `EasyAnimatePipeline`
-(easyanimate/pipeline/pipeline_easyanimate.py:170-1160, executed unmodified from /root/reference) with the third-party
+(easyanimate/pipeline/pipeline_easyanimate.py:175-1148, executed unmodified from /root/reference) with the third-party
 `diffusers` names it imports supplied by oracle/_refshim (DiffusionPipeline plumbing, FlowMatchEulerDiscreteScheduler,
 get_3d_rotary_pos_embed, randn_tensor; everything else a placeholder).
 
@@ -59,7 +59,7 @@ def _scheduler():
 
 
 def reference_inpaint_pipeline(transformer, vae, scheduler=None):
-    """The reference's `EasyAnimateInpaintPipeline` (pipeline_easyanimate_inpaint.py:243-1560; predict_i2v.py builds it), no
+    """The reference's `EasyAnimateInpaintPipeline` (pipeline_easyanimate_inpaint.py:245-1604; predict_i2v.py builds it), no
     CLIP image encoder (V5.1: enable_clip_in_inpaint false), text encoders = None."""
     _reference_pipeline_module()
     mod = importlib.import_module("easyanimate.pipeline.pipeline_easyanimate_inpaint")
@@ -68,7 +68,7 @@ def reference_inpaint_pipeline(transformer, vae, scheduler=None):
 
 
 def reference_control_pipeline(transformer, vae, scheduler=None):
-    """The reference's `EasyAnimateControlPipeline` (pipeline_easyanimate_control.py:214-1290; predict_v2v_control.py builds it)."""
+    """The reference's `EasyAnimateControlPipeline` (pipeline_easyanimate_control.py:200-1282; predict_v2v_control.py builds it)."""
     _reference_pipeline_module()
     mod = importlib.import_module("easyanimate.pipeline.pipeline_easyanimate_control")
     return mod.EasyAnimateControlPipeline(vae=vae, text_encoder=None, tokenizer=_tokenizer(), text_encoder_2=None, tokenizer_2=None,

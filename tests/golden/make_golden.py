@@ -212,7 +212,7 @@ def pipeline_case_inputs(seed=43):
 
 
 def make_pipeline_reference():
-    """`pipe_ref_t2v.safetensors`: the REFERENCE's own EasyAnimatePipeline.__call__ (pipeline_easyanimate.py:764-1160, through
+    """`pipe_ref_t2v.safetensors`: the REFERENCE's own EasyAnimatePipeline.__call__ (pipeline_easyanimate.py:769-1148, through
     oracle/ref_pipeline.py) over the reference's own transformer and VAE: 4 CFG flow-matching steps + decode_latents, once in
     bf16 (the execution the product reproduces) and once in fp32 with the same bf16-rounded weights (the truth of the
     three-way criterion).  Stored: the inputs, the final latents of both runs, the frames of both runs."""

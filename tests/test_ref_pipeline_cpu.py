@@ -1,5 +1,5 @@
 """SURVEY.md section 8b, the boundary's strongest proof available without a GPU: the REFERENCE's own
-`EasyAnimatePipeline.__call__` (easyanimate/pipeline/pipeline_easyanimate.py:764-1160, executed unmodified from
+`EasyAnimatePipeline.__call__` (easyanimate/pipeline/pipeline_easyanimate.py:769-1148, executed unmodified from
 /root/reference through oracle/ref_pipeline.py) driving
 
   (1) the reference's own transformer + VAE  -> pins oracle.dit.denoise_loop + oracle.vae decode + the decode_latents tail
@@ -121,7 +121,7 @@ def _i2v_inputs(seed=9):
 
 
 def test_reference_inpaint_pipeline_drives_the_product_modules(monkeypatch):
-    """`EasyAnimateInpaintPipeline.__call__` (pipeline_easyanimate_inpaint.py:978-1560), unmodified: VaeImageProcessor ->
+    """`EasyAnimateInpaintPipeline.__call__` (pipeline_easyanimate_inpaint.py:978-1604), unmodified: VaeImageProcessor ->
     masked video -> `vae.encode(...)[0].mode()` * scaling_factor -> resize_mask -> inpaint_latents (1 + 16 channels) -> denoise
     loop with `inpaint_latents=` -> decode_latents.  Once over the reference's transformer + VAE, once over the product's
     (kernels = torch stand-ins): same start noise (seeded generator), same frames up to bf16 round-off."""
@@ -167,7 +167,7 @@ CONTROL_CFG = dict(CFG, in_channels=48, time_position_encoding_type="3d_rope", a
 
 @pytest.mark.parametrize("with_ref_image", [True, False])
 def test_reference_control_pipeline_drives_the_product_modules(monkeypatch, with_ref_image):
-    """`EasyAnimateControlPipeline.__call__` (pipeline_easyanimate_control.py:830-1290), unmodified: control video ->
+    """`EasyAnimateControlPipeline.__call__` (pipeline_easyanimate_control.py:833-1282), unmodified: control video ->
     `vae.encode` -> control_latents (16 channels) + the reference image's latent in frame 0 of 16 more channels
     (add_ref_latent_in_control_model) -> `transformer(..., control_latents=)` -> decode_latents."""
     import easyanimate_b200.autoencoder_magvit as A
