@@ -171,6 +171,6 @@ class EasyAnimateSampler:
                        to_host: bool = True) -> torch.Tensor:
         """pipeline_easyanimate.py:722-742: /scaling_factor -> vae.decode -> clamp(-1,1) -> /2+.5 -> clamp(0,1) ->
         `.cpu().float()`: returns the [B,3,T,H,W] float32 frames in (pinned) HOST memory by default - `torch.from_numpy` /
-        `.numpy()` views of it are what the reference pipeline hands back as `.frames` (:1139-1149).  No torch arithmetic:
+        `.numpy()` views of it are what the reference pipeline hands back as `.frames` (:1136-1148).  No torch arithmetic:
         the scale rides in the latent-preparation kernel, the tail is `ea_frames_out` (AutoencoderKLMagvit.decode_scaled)."""
         return self.vae.decode_scaled(latents.to(bf16), out=out, dtype=dtype, to_host=to_host)

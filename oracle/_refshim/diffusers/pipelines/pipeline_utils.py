@@ -1,5 +1,5 @@
 """diffusers.pipelines.pipeline_utils.DiffusionPipeline: what EasyAnimatePipeline.__init__ / __call__ use of it
-(pipeline_easyanimate.py:221-240,895-1160): register_modules, _execution_device, progress_bar, maybe_free_model_hooks.
+(pipeline_easyanimate.py:221-240,895-1148): register_modules, _execution_device, progress_bar, maybe_free_model_hooks.
 No hub / offload / device-map machinery."""
 import contextlib
 

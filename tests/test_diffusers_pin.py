@@ -7,7 +7,7 @@ published functions that do exist on this box:
     interpolation_scale / base_size) and transformers' MAE original (models/vit_mae/modeling_vit_mae.py);
   * `get_timestep_embedding`   <- the reference's vendored DDPM original (easyanimate/vae/ldm/modules/diffusionmodules/model.py:
     12-32 = flip_sin_to_cos False, downscale_freq_shift 1), which fixes the exponent / (half_dim - shift) form and the sin|cos
-    order that `flip_sin_to_cos=True, downscale_freq_shift=0` (transformer3d.py:1401) then permutes;
+    order that `flip_sin_to_cos=True, downscale_freq_shift=0` (transformer3d.py:1399, ctor defaults :1365,1377) then permutes;
   * GELU(tanh), SiLU, LayerNorm, scaled_dot_product_attention are torch's own kernels in diffusers too (nothing to restate).
 Part B runs only where a real `diffusers` is importable (skipped otherwise - on both boxes of this build) and compares every
 restated primitive with the real class / function: scheduler, 3-D RoPE table, Timesteps, apply_rotary_emb, AdaLayerNorm,
@@ -90,7 +90,7 @@ def test_timestep_embedding_matches_the_references_vendored_ddpm_original(dim):
         # same formula, different association of the fp32 products (DDPM: arange * (-log/(h-1)); diffusers: (-log * arange)/(h-1)):
         # arguments up to 1000 rad -> 1e-7 relative is ~1e-4 absolute in sin / cos
         assert torch.allclose(f(t, dim, flip_sin_to_cos=False, downscale_freq_shift=1), want, rtol=0, atol=3e-4)
-        # the EasyAnimate configuration (transformer3d.py:1401 Timesteps(inner_dim, True, 0)): cos | sin, exponent / half_dim
+        # the EasyAnimate configuration (transformer3d.py:1399 Timesteps(inner_dim, flip_sin_to_cos=True, freq_shift=0)): cos | sin, exponent / half_dim
         half = dim // 2
         freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32) / half)
         arg = t[:, None].float() * freqs[None]
