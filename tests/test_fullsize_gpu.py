@@ -83,7 +83,7 @@ def test_dit_block_full_token_count_is_identity_when_gates_are_zero():
 
 def test_vae_decode_720p_is_causal_in_time():
     """CausalConv3d / per-frame GroupNorm / per-frame attention: decoding the first k latent frames gives exactly the
-    first 4(k-1)+1 video frames of decoding all 13 (omnigen_enc_dec.py:586-680 processes latent frames in order with a
+    first 4(k-1)+1 video frames of decoding all 13 (omnigen_enc_dec.py:586-677 processes latent frames in order with a
     causal cache) - at the full 90x160 latent, untiled."""
     from easyanimate_b200.autoencoder_magvit import AutoencoderKLMagvit
     with torch.device("cuda"):
