@@ -266,3 +266,19 @@ def test_teacache_inside_the_pipeline_call_matches_the_reference_pipeline(on_cpu
     got = EasyAnimatePipeline(vae=v, transformer=t)(**kw).frames
     assert 0 < skipped_ref < steps and t.teacache.skipped == 2 * skipped_ref
     _same(got, want)
+
+
+def test_two_videos_per_prompt(on_cpu):
+    """num_images_per_prompt = 2: embeddings repeated, a batch of two latents (drawn at once, or from one generator per sample)."""
+    from easyanimate_b200 import EasyAnimatePipeline
+    t, v = _modules(on_cpu)
+    pe, ne = _embeds(torch.Generator().manual_seed(31))
+    kw = dict(video_length=FRAMES, height=H, width=W, num_inference_steps=2, guidance_scale=6.0, num_images_per_prompt=2,
+              **_mask_kw(pe, ne))
+    ref, pipe = ref_pipeline.reference_pipeline(t, v), EasyAnimatePipeline(vae=v, transformer=t)
+    want = ref(generator=torch.Generator().manual_seed(32), **kw).frames
+    got = pipe(generator=torch.Generator().manual_seed(32), **kw).frames
+    assert got.shape == (2, 3, FRAMES, H, W)
+    _same(got, want)
+    with pytest.raises(ValueError, match="list of generators"):
+        pipe(generator=[torch.Generator().manual_seed(1)] * 3, **kw)
