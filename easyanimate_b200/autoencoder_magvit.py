@@ -526,6 +526,15 @@ class AutoencoderKLMagvit(nn.Module, ConfigMixinLite):
     def _clear_conv_cache(self):  # the whole-sequence kernels keep no cache; kept for API compatibility
         return None
 
+    def invalidate_weight_caches(self) -> None:
+        """Drop the packed convolution weights and fused q/k/v copies (rebuilt on the next call); needed only after edits of
+        `weight.data` that bypass the parameters' version counters (see EasyAnimateTransformer3DModel.invalidate_weight_caches)."""
+        for m in self.modules():
+            if isinstance(m, _PackedConv):
+                m._packed = None
+            elif isinstance(m, _SpatialAttention):
+                m._fused = None
+
     # ----------------------------------------------------------------------------------------------------------
     @classmethod
     def from_pretrained(cls, pretrained_model_path, subfolder=None, **vae_additional_kwargs):

@@ -405,6 +405,19 @@ class EasyAnimateTransformer3DModel(nn.Module, ConfigMixinLite):
     def _set_gradient_checkpointing(self, module, value=False):
         self.gradient_checkpointing = value
 
+    def invalidate_weight_caches(self) -> None:
+        """Drop every derived copy of the parameters (fused q/k/v weights, the patch-embed GEMM operands, the fp8 staging block).
+        They are rebuilt on the next forward.  Needed only after edits that bypass the parameters' version counters - the
+        reference's LoRA merge / unmerge writes `layer.weight.data += ...` (utils/lora_utils.py:425-429,487-491), which neither
+        moves the storage nor bumps `_version`; `load_state_dict`, `.to(...)` and in-place ops on the parameters themselves are
+        detected without this call."""
+        for m in self.modules():
+            if isinstance(m, _Attention):
+                m._fused = None
+        self._proj_w_cache.clear()
+        self._ref_pos_cache = None
+        self._fp8 = None
+
     def _fp8_staging(self) -> _Fp8Staging:
         key = ops.param_key(self.proj.weight, self.proj_out.weight)
         if self._fp8 is None or self._fp8[0] != key:

@@ -247,3 +247,35 @@ def test_control_ref_and_clip_tokens_host_logic(monkeypatch, with_clip):
     assert _rel(got, ref) < 2e-2 and _rel(got, plain) > 2 * _rel(got, ref)  # (the reference-image tokens do change the result)
     with pytest.raises(ValueError):
         ours(lat, t, encoder_hidden_states=enc, image_rotary_emb=rope, clip_encoder_hidden_states=torch.zeros(2, 5, 96).to(bf16))
+
+
+def test_weight_data_edits_need_invalidate_weight_caches(monkeypatch):
+    """The reference's LoRA merge writes `layer.weight.data += delta` (utils/lora_utils.py:425-429): no new storage, no version
+    bump, so the fused q/k/v copy of an attention module cannot notice it.  `invalidate_weight_caches()` is the documented
+    hand-shake; parameter updates that go through the version counter (load_state_dict, in-place ops) are picked up by themselves."""
+    cpu_ops.install(monkeypatch)
+    ob, ours = _models(CFG)
+    g = torch.Generator().manual_seed(8)
+    lat = torch.randn(1, 16, 2, 8, 12, generator=g).to(bf16)
+    enc = (torch.randn(1, 9, 128, generator=g) * 3).to(bf16)
+    t = torch.tensor([500.0]).to(bf16)
+    rope = dit.rope_for_video(64, 96, 2)
+
+    def run(m):
+        with torch.no_grad():
+            out = m(lat, t, encoder_hidden_states=enc, image_rotary_emb=rope, return_dict=False)
+        return out[0]
+
+    base = run(ours)
+    w = ours.transformer_blocks[0].attn1.to_q.weight
+    delta = torch.randn(w.shape, generator=g).to(bf16) * 0.05
+    original = w.detach().clone()
+    w.data += delta                                   # what merge_lora does
+    ob.transformer_blocks[0].attn1.to_q.weight.data += delta
+    assert torch.equal(run(ours), base)               # stale fused copy: the edit is invisible ...
+    ours.invalidate_weight_caches()
+    merged = run(ours)
+    assert not torch.equal(merged, base) and _rel(merged, run(ob)) < 2e-2  # ... until the caches are dropped
+    with torch.no_grad():
+        w.copy_(original)                             # an in-place op on the parameter itself bumps its version: noticed
+    assert torch.equal(run(ours), base)
