@@ -202,3 +202,53 @@ def test_reference_control_pipeline_drives_the_product_modules(monkeypatch, with
     assert frames.shape == want.shape == (1, 3, FRAMES, H, W) and frames.dtype == torch.float32
     rel = ((frames - want).norm() / want.norm()).item()
     assert rel < 3e-2, rel
+
+
+def test_reference_merge_lora_walks_the_product_transformer(monkeypatch):
+    """utils/lora_utils.py:369-431 `merge_lora` (lifted out of the reference file, executed unmodified) resolves
+    `lora_unet__transformer_blocks_0_attn1_to_q`-style keys by attribute walks over `pipeline.transformer` and edits
+    `layer.weight.data`: the product transformer has the same module tree, so the same LoRA file merges into it; after
+    `invalidate_weight_caches()` its forward equals the forward of the reference transformer with the same LoRA merged."""
+    import ast
+    import types
+    from collections import defaultdict
+    from easyanimate_b200.transformer3d import EasyAnimateTransformer3DModel
+    from oracle import ref_dit
+    path = f"{ref_pipeline.REFERENCE_ROOT}/easyanimate/utils/lora_utils.py"
+    fn = [n for n in ast.parse(open(path).read()).body if isinstance(n, ast.FunctionDef) and n.name == "merge_lora"]
+    ns = {"torch": torch, "defaultdict": defaultdict, "load_file": None}
+    exec(compile(ast.Module(body=fn, type_ignores=[]), path, "exec"), ns)
+    cpu_ops.install(monkeypatch)
+    cfg = dict(CFG, time_position_encoding_type="3d_rope")
+    ob = dit.init_weights_(dit.OracleTransformer3D(**CFG), 81).to(bf16)
+    ours = EasyAnimateTransformer3DModel(**cfg).to(bf16)
+    ours.load_state_dict(ob.state_dict(), strict=True)
+    rt = ref_dit.reference_transformer(**cfg).eval().to(bf16)
+    rt.load_state_dict(ob.state_dict(), strict=True)
+    g = torch.Generator().manual_seed(82)
+    lora, d = {}, CFG["num_attention_heads"] * 64
+    for name, (o, i) in {"transformer_blocks_0_attn1_to_q": (d, d), "transformer_blocks_1_attn2_to_v": (d, d),
+                         "transformer_blocks_1_ff_net_2": (d, 4 * d), "transformer_blocks_0_txt_ff_net_0_proj": (4 * d, d)}.items():
+        lora[f"lora_unet__{name}.lora_down.weight"] = torch.randn(4, i, generator=g) * 0.1
+        lora[f"lora_unet__{name}.lora_up.weight"] = torch.randn(o, 4, generator=g) * 0.1
+        lora[f"lora_unet__{name}.alpha"] = torch.tensor(2.0)
+    lat = torch.randn(1, 16, LF, H // 8, W // 8, generator=g).to(bf16)
+    enc = (torch.randn(1, 9, 128, generator=g) * 3).to(bf16)
+    t = torch.tensor([700.0]).to(bf16)
+    rope = dit.rope_for_video(H, W, LF)
+
+    def run(m):
+        with torch.no_grad():
+            return m(lat, t, encoder_hidden_states=enc, image_rotary_emb=rope, return_dict=False)[0]
+
+    before = run(ours)
+    for m in (ours, rt):
+        ns["merge_lora"](types.SimpleNamespace(transformer=m, text_encoder=None), None, 0.8, state_dict=dict(lora), transformer_only=True)
+    ours.invalidate_weight_caches()
+    after, want = run(ours), run(rt)
+    theirs = rt.state_dict()
+    for k, a in ours.state_dict().items():
+        assert torch.equal(a, theirs[k]), k  # the same edits landed in the same parameters
+    assert not torch.equal(theirs["transformer_blocks.0.attn1.to_q.weight"], ob.state_dict()["transformer_blocks.0.attn1.to_q.weight"])
+    rel = ((after.float() - want.float()).norm() / want.float().norm()).item()
+    assert rel < 2e-2 and not torch.equal(after, before), rel
