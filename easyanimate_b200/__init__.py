@@ -7,7 +7,7 @@ from . import _lib  # noqa: F401  (fails loudly if the CUDA extension has not be
 from .autoencoder_magvit import AutoencoderKLMagvit
 from .pipeline import EasyAnimateSampler, rope_table
 from .pipelines import (EasyAnimateControlPipeline, EasyAnimateInpaintPipeline, EasyAnimatePipeline,
-                        EasyAnimatePipelineOutput)
+                        EasyAnimatePipelineOutput, load_pipeline)
 from .scheduler import FlowMatchEulerDiscreteScheduler
 from .transformer3d import EasyAnimateTransformer3DModel
 
@@ -16,4 +16,4 @@ name_to_autoencoder_magvit = {"AutoencoderKLMagvit": AutoencoderKLMagvit}
 
 __all__ = ["AutoencoderKLMagvit", "EasyAnimateControlPipeline", "EasyAnimateInpaintPipeline", "EasyAnimatePipeline",
            "EasyAnimatePipelineOutput", "EasyAnimateSampler", "EasyAnimateTransformer3DModel", "FlowMatchEulerDiscreteScheduler",
-           "name_to_autoencoder_magvit", "name_to_transformer3d", "rope_table"]
+           "load_pipeline", "name_to_autoencoder_magvit", "name_to_transformer3d", "rope_table"]

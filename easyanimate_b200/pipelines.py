@@ -530,3 +530,73 @@ class EasyAnimateControlPipeline(_B200PipelineBase):
         latents = self._denoise(latents, pe, ne, height, width, first, steps, guidance_scale, control_latents=control,
                                 callback_on_step_end=callback_on_step_end, callback_tensor_inputs=callback_on_step_end_tensor_inputs)
         return self._finish(latents, output_type, return_dict)
+
+
+def load_pipeline(model_name: str, config: Union[str, dict, None] = None, weight_dtype=bf16, device="cuda",
+                  transformer_path: Optional[str] = None, vae_path: Optional[str] = None, load_text_encoder: bool = True,
+                  cfg_group=None):
+    """The loading sequence of predict_t2v.py:94-255 / predict_i2v.py for a released EasyAnimateV5.1 directory
+    (`transformer/`, `vae/`, `scheduler/`, `tokenizer/`, `text_encoder/`), ending in the pipeline object those scripts build:
+    `EasyAnimateInpaintPipeline` when the transformer has more input channels than the VAE has latent channels (the InP /
+    I2V checkpoints), else `EasyAnimatePipeline`.
+
+    config: the model YAML the scripts read (config/easyanimate_video_v5.1_magvit_qwen.yaml) as a path or a dict with
+    `transformer_additional_kwargs` / `vae_kwargs` / `text_encoder_kwargs`; None = the V5.1 values.
+    transformer_path / vae_path: optional fine-tuned weights loaded over the released ones (non-strict, like the scripts).
+    load_text_encoder: the Qwen2-VL tokenizer and text encoder through `transformers` when their folders exist; without them
+    the pipeline takes `prompt_embeds` (+ masks) instead of prompt strings."""
+    import os
+
+    from .autoencoder_magvit import AutoencoderKLMagvit
+    from .transformer3d import EasyAnimateTransformer3DModel
+
+    if config is None:
+        config = {"transformer_additional_kwargs": {"transformer_type": "EasyAnimateTransformer3DModel", "after_norm": False,
+                                                    "time_position_encoding_type": "3d_rope", "resize_inpaint_mask_directly": True,
+                                                    "enable_text_attention_mask": True, "enable_clip_in_inpaint": False,
+                                                    "add_ref_latent_in_control_model": True},
+                  "vae_kwargs": {"vae_type": "AutoencoderKLMagvit", "mini_batch_encoder": 4, "mini_batch_decoder": 1,
+                                 "slice_mag_vae": False, "slice_compression_vae": False, "cache_compression_vae": False,
+                                 "cache_mag_vae": True},
+                  "text_encoder_kwargs": {"enable_multi_text_encoder": False, "replace_t5_to_llm": True}}
+    elif isinstance(config, str):
+        import yaml
+        with open(config) as f:
+            config = yaml.safe_load(f)
+    tkw = dict(config.get("transformer_additional_kwargs", {}))
+    if tkw.get("transformer_type", "EasyAnimateTransformer3DModel") != "EasyAnimateTransformer3DModel":
+        raise NotImplementedError(f"transformer_type {tkw.get('transformer_type')}: only the V5 / V5.1 EasyAnimateTransformer3DModel")
+    if config.get("vae_kwargs", {}).get("vae_type", "AutoencoderKLMagvit") != "AutoencoderKLMagvit":
+        raise NotImplementedError("only the MagViT VAE (vae_type AutoencoderKLMagvit)")
+    if config.get("text_encoder_kwargs", {}).get("enable_multi_text_encoder", False):
+        raise NotImplementedError("enable_multi_text_encoder (EasyAnimate V5 Bert + T5) is not carried over")
+
+    def overlay(module, path):
+        if path.endswith("safetensors"):
+            from safetensors.torch import load_file
+            state = load_file(path)
+        else:
+            state = torch.load(path, map_location="cpu")
+        state = state["state_dict"] if "state_dict" in state else state
+        return module.load_state_dict(state, strict=False)
+
+    transformer = EasyAnimateTransformer3DModel.from_pretrained_2d(model_name, subfolder="transformer",
+                                                                   transformer_additional_kwargs=tkw, torch_dtype=weight_dtype,
+                                                                   low_cpu_mem_usage=True)
+    if transformer_path is not None:
+        overlay(transformer, transformer_path)
+    vae = AutoencoderKLMagvit.from_pretrained(model_name, subfolder="vae",
+                                              vae_additional_kwargs=dict(config.get("vae_kwargs", {}))).to(weight_dtype)
+    if vae_path is not None:
+        overlay(vae, vae_path)
+    tokenizer = text_encoder = None
+    if load_text_encoder and os.path.isdir(os.path.join(model_name, "tokenizer")) and os.path.isdir(os.path.join(model_name, "text_encoder")):
+        from transformers import Qwen2Tokenizer, Qwen2VLForConditionalGeneration
+        tokenizer = Qwen2Tokenizer.from_pretrained(os.path.join(model_name, "tokenizer"))
+        text_encoder = Qwen2VLForConditionalGeneration.from_pretrained(os.path.join(model_name, "text_encoder"),
+                                                                       torch_dtype=weight_dtype).to(device)
+    scheduler = (FlowMatchEulerDiscreteScheduler.from_pretrained(model_name, subfolder="scheduler")
+                 if os.path.isfile(os.path.join(model_name, "scheduler", "scheduler_config.json")) else FlowMatchEulerDiscreteScheduler())
+    kind = EasyAnimateInpaintPipeline if transformer.config.in_channels != vae.config.latent_channels else EasyAnimatePipeline
+    return kind(vae=vae.to(device), transformer=transformer.to(device), scheduler=scheduler, tokenizer=tokenizer,
+                text_encoder=text_encoder, cfg_group=cfg_group)

@@ -38,6 +38,20 @@ class FlowMatchEulerDiscreteScheduler:
         self._step_index: Optional[int] = None
         self.num_inference_steps: Optional[int] = None
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, subfolder: Optional[str] = None, **overrides):
+        """`FlowMatchEulerDiscreteScheduler.from_pretrained(model_name, subfolder="scheduler")` (predict_t2v.py:225-231): the
+        released `scheduler/scheduler_config.json` (shift, use_dynamic_shifting, ...); unknown keys are ignored like diffusers'
+        `from_config` ignores them."""
+        import inspect
+        import json
+        import os
+        path = pretrained_model_name_or_path if subfolder is None else os.path.join(pretrained_model_name_or_path, subfolder)
+        with open(os.path.join(path, "scheduler_config.json")) as f:
+            cfg = json.load(f)
+        accepted = set(inspect.signature(cls.__init__).parameters) - {"self"}
+        return cls(**{**{k: v for k, v in cfg.items() if k in accepted}, **{k: v for k, v in overrides.items() if k in accepted}})
+
     @property
     def step_index(self):
         return self._step_index

@@ -282,3 +282,43 @@ def test_two_videos_per_prompt(on_cpu):
     _same(got, want)
     with pytest.raises(ValueError, match="list of generators"):
         pipe(generator=[torch.Generator().manual_seed(1)] * 3, **kw)
+
+
+def test_load_pipeline_follows_the_predict_scripts_loading_sequence(on_cpu, tmp_path):
+    """predict_t2v.py:94-255 on a released-layout directory (transformer/, vae/, scheduler/ with config.json + safetensors):
+    `load_pipeline` returns the pipeline class the scripts pick (InP checkpoint -> inpaint pipeline), with the scheduler of
+    scheduler_config.json, and its call equals the call of a pipeline built by hand from the same weights."""
+    import json
+    from safetensors.torch import save_file
+    from easyanimate_b200 import EasyAnimateInpaintPipeline, EasyAnimatePipeline, load_pipeline
+    t, v = _modules(on_cpu, in_channels=33, seeds=(91, 92), resize_inpaint_mask_directly=True, enable_clip_in_inpaint=False)
+    for name, module in (("transformer", t), ("vae", v)):
+        d = tmp_path / name
+        d.mkdir()
+        (d / "config.json").write_text(json.dumps(dict(module.config)))
+        save_file({k: x.detach().contiguous() for k, x in module.state_dict().items()}, str(d / "diffusion_pytorch_model.safetensors"))
+    (tmp_path / "scheduler").mkdir()
+    (tmp_path / "scheduler" / "scheduler_config.json").write_text(json.dumps(
+        {"_class_name": "FlowMatchEulerDiscreteScheduler", "_diffusers_version": "0.31.0", "num_train_timesteps": 1000, "shift": 3.0,
+         "use_dynamic_shifting": False, "base_shift": 0.5, "max_shift": 1.15, "base_image_seq_len": 256, "max_image_seq_len": 4096}))
+    pipe = load_pipeline(str(tmp_path), device="cpu")
+    assert isinstance(pipe, EasyAnimateInpaintPipeline) and pipe.scheduler.config.shift == 3.0 and pipe.tokenizer is None
+    assert pipe.transformer.dtype == bf16 and pipe.transformer.resize_inpaint_mask_directly and pipe.vae.cache_mag_vae
+    for k, x in t.state_dict().items():
+        assert torch.equal(pipe.transformer.state_dict()[k], x), k
+    g = torch.Generator().manual_seed(93)
+    video = torch.tile(torch.rand(1, 3, 1, H, W, generator=g), [1, 1, FRAMES, 1, 1])
+    mask = torch.zeros_like(video[:, :1])
+    mask[:, :, 1:] = 255
+    pe, ne = _embeds(g)
+    kw = dict(video_length=FRAMES, video=video, mask_video=mask, height=H, width=W, num_inference_steps=2, guidance_scale=6.0,
+              **_mask_kw(pe, ne))
+    from easyanimate_b200 import FlowMatchEulerDiscreteScheduler
+    by_hand = EasyAnimateInpaintPipeline(vae=v, transformer=t, scheduler=FlowMatchEulerDiscreteScheduler(shift=3.0))
+    _same(pipe(generator=torch.Generator().manual_seed(94), **kw).frames, by_hand(generator=torch.Generator().manual_seed(94), **kw).frames)
+    # a 16-channel checkpoint gives the text-to-video pipeline
+    t16, _ = _modules(on_cpu, seeds=(95, 92))
+    (tmp_path / "transformer" / "config.json").write_text(json.dumps(dict(t16.config)))
+    save_file({k: x.detach().contiguous() for k, x in t16.state_dict().items()},
+              str(tmp_path / "transformer" / "diffusion_pytorch_model.safetensors"))
+    assert type(load_pipeline(str(tmp_path), device="cpu")) is EasyAnimatePipeline
