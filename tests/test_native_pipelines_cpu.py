@@ -322,3 +322,17 @@ def test_load_pipeline_follows_the_predict_scripts_loading_sequence(on_cpu, tmp_
     save_file({k: x.detach().contiguous() for k, x in t16.state_dict().items()},
               str(tmp_path / "transformer" / "diffusion_pytorch_model.safetensors"))
     assert type(load_pipeline(str(tmp_path), device="cpu")) is EasyAnimatePipeline
+
+
+@pytest.mark.parametrize("video_length,h,w", [(1, 64, 96), (9, 48, 80), (5, 70, 100)])
+def test_t2v_edge_shapes(on_cpu, video_length, h, w):
+    """A single image (video_length 1 -> one latent frame), 1 + 8 frames, and a size that is not a multiple of 16 (both pipelines
+    round it down: pipeline_easyanimate.py:874-876)."""
+    from easyanimate_b200 import EasyAnimatePipeline
+    t, v = _modules(on_cpu)
+    pe, ne = _embeds(torch.Generator().manual_seed(41))
+    kw = dict(video_length=video_length, height=h, width=w, num_inference_steps=2, guidance_scale=6.0, **_mask_kw(pe, ne))
+    want = ref_pipeline.reference_pipeline(t, v)(generator=torch.Generator().manual_seed(42), **kw).frames
+    got = EasyAnimatePipeline(vae=v, transformer=t)(generator=torch.Generator().manual_seed(42), **kw).frames
+    assert got.shape == (1, 3, video_length, h // 16 * 16, w // 16 * 16)
+    _same(got, want)
