@@ -336,3 +336,19 @@ def test_t2v_edge_shapes(on_cpu, video_length, h, w):
     got = EasyAnimatePipeline(vae=v, transformer=t)(generator=torch.Generator().manual_seed(42), **kw).frames
     assert got.shape == (1, 3, video_length, h // 16 * 16, w // 16 * 16)
     _same(got, want)
+
+
+def test_inpaint_pipeline_with_vae_encoded_mask(on_cpu):
+    """resize_inpaint_mask_directly = False (EasyAnimate V5 InP: 16 + 16 + 16 input channels): the mask itself goes through
+    `vae.encode` (pipeline_easyanimate_inpaint.py:1364-1376, 781-792) instead of being resized."""
+    from easyanimate_b200 import EasyAnimateInpaintPipeline
+    t, v = _modules(on_cpu, in_channels=48, seeds=(77, 78), resize_inpaint_mask_directly=False, enable_clip_in_inpaint=False)
+    g = torch.Generator().manual_seed(14)
+    video = torch.rand(1, 3, FRAMES, H, W, generator=g)
+    mask = torch.zeros_like(video[:, :1])
+    mask[:, :, 2:, :, W // 2:] = 255
+    pe, ne = _embeds(g)
+    kw = dict(video_length=FRAMES, video=video, mask_video=mask, height=H, width=W, num_inference_steps=2, guidance_scale=6.0,
+              **_mask_kw(pe, ne))
+    want = ref_pipeline.reference_inpaint_pipeline(t, v)(generator=torch.Generator().manual_seed(15), **kw).frames
+    _same(EasyAnimateInpaintPipeline(vae=v, transformer=t)(generator=torch.Generator().manual_seed(15), **kw).frames, want)
