@@ -352,3 +352,23 @@ def test_inpaint_pipeline_with_vae_encoded_mask(on_cpu):
               **_mask_kw(pe, ne))
     want = ref_pipeline.reference_inpaint_pipeline(t, v)(generator=torch.Generator().manual_seed(15), **kw).frames
     _same(EasyAnimateInpaintPipeline(vae=v, transformer=t)(generator=torch.Generator().manual_seed(15), **kw).frames, want)
+
+
+def test_inpaint_reference_video_noise_with_sampled_strength(on_cpu):
+    """noise_aug_strength = None: one noise level per sample drawn from exp(N(-3, 0.5)) with the GLOBAL generator
+    (pipeline_easyanimate_inpaint.py:153-157), then the noise itself with the call's generator."""
+    from easyanimate_b200 import EasyAnimateInpaintPipeline
+    t, v = _modules(on_cpu, in_channels=33, seeds=(73, 74), resize_inpaint_mask_directly=True, enable_clip_in_inpaint=False,
+                    add_noise_in_inpaint_model=True)
+    g = torch.Generator().manual_seed(16)
+    video = torch.rand(1, 3, FRAMES, H, W, generator=g)
+    mask = torch.zeros_like(video[:, :1])
+    mask[:, :, 1:] = 255
+    pe, ne = _embeds(g)
+    kw = dict(video_length=FRAMES, video=video, mask_video=mask, height=H, width=W, num_inference_steps=2, guidance_scale=6.0,
+              noise_aug_strength=None, **_mask_kw(pe, ne))
+    torch.manual_seed(17)
+    want = ref_pipeline.reference_inpaint_pipeline(t, v)(generator=torch.Generator().manual_seed(18), **kw).frames
+    torch.manual_seed(17)
+    got = EasyAnimateInpaintPipeline(vae=v, transformer=t)(generator=torch.Generator().manual_seed(18), **kw).frames
+    _same(got, want)
