@@ -112,3 +112,15 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
     # and the header declares no struct the binding does not mirror
     hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "ea_b200.h")).read(), flags=re.S)
     assert sorted(re.findall(r"^\}\s*(ea_[a-z0-9_]+);", hdr, flags=re.M)) == sorted(pairs)
+
+
+def test_import_fails_loudly_without_the_built_library(tmp_path):
+    """No CPU / PyTorch fallback: a copy of the package WITHOUT libea_b200.so cannot even be imported."""
+    import shutil
+    import subprocess
+    import sys
+    shutil.copytree(os.path.join(ROOT, "easyanimate_b200"), str(tmp_path / "easyanimate_b200"),
+                    ignore=shutil.ignore_patterns("*.so", "_build", "__pycache__", "csrc"))
+    r = subprocess.run([sys.executable, "-c", "import easyanimate_b200"], cwd=str(tmp_path), capture_output=True, text=True,
+                       env={**os.environ, "PYTHONPATH": str(tmp_path)})
+    assert r.returncode != 0 and "ImportError" in r.stderr and "no CPU/PyTorch fallback" in r.stderr
